@@ -1,0 +1,137 @@
+/*
+ * repyolo_b200 -- C ABI of the B200-native Rep-YOLO deploy path (fused conv stack -> Detect decode -> NMS).
+ *
+ * The reference (DrLSB/Rep-YOLO) is pure Python/PyTorch and has no plugin / FFI layer; the drop-in boundary is the
+ * Python signatures listed below.  This header is what a host-language binding (ctypes in `rep-yolo_b200/`) binds to:
+ * plain pointers and sizes, no torch types, no exceptions, `int` status (0 = ok, see ry_last_error()).
+ * All data pointers are DEVICE pointers unless the name says `host`; `stream` is a cudaStream_t passed as void*.
+ * No entry point allocates or synchronises inside the hot calls (ry_forward / ry_run_ops / ry_nms); the caller
+ * provides the workspace (ry_plan_workspace_bytes / ry_nms_workspace_bytes).
+ *
+ * Reference interfaces replaced (file:line relative to the reference repo):
+ *   ry_plan_create      <- Model.fuse()              models/yolo.py:681-704  (graph rewrite result: the fused op list;
+ *                          the fold arithmetic itself -- common.py:597-657, 3436-3517, torch_utils.py:181-201,
+ *                          yolo.py:170-182 -- runs on the host in rep-yolo_b200/fold.py and hands fp32 OIHW weights here)
+ *   ry_forward          <- Model.forward / forward_once + IDetect.fuseforward   models/yolo.py:569-619, 135-168
+ *   ry_run_ops          <- one top-level module of forward_once (teacher-forced module parity; yolo.py:613)
+ *   ry_nms              <- non_max_suppression       utils/general.py:953-1045 (+ xywh2xyxy :265-272,
+ *                          torchvision.ops.nms call site :1029)
+ */
+#ifndef REPYOLO_B200_H
+#define REPYOLO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RY_ABI_VERSION 1
+
+typedef struct ry_plan ry_plan;
+
+/* ---- plan IR ------------------------------------------------------------------------------------------------ */
+
+enum ry_dtype { RY_BF16 = 0, RY_F32 = 1 };
+
+enum ry_tensor_kind {
+    RY_T_MAP = 0,      /* activation map, NHWC: [B, H>>level, W>>level, channels] */
+    RY_T_VEC = 1,      /* per-image vector:     [B, channels]                      */
+    RY_T_EXTERNAL = 2  /* bound per call (image / pred / raw heads), see slot      */
+};
+
+enum ry_external_slot { RY_X_IMAGE = 0, RY_X_PRED = 1, RY_X_RAW0 = 2, RY_X_RAW1 = 3, RY_X_RAW2 = 4 };
+
+typedef struct ry_tensor_desc {
+    int32_t kind;      /* ry_tensor_kind */
+    int32_t dtype;     /* ry_dtype */
+    int32_t channels;
+    int32_t level;     /* log2 of the spatial down-scale w.r.t. the input image (MAP only) */
+    int32_t slot;      /* ry_external_slot (EXTERNAL only) */
+    int32_t pad_;
+} ry_tensor_desc;
+
+typedef struct ry_view {   /* a channel range of a tensor */
+    int32_t tensor;        /* index into the tensor table, -1 = none */
+    int32_t c_off;
+    int32_t c_len;
+} ry_view;
+
+enum ry_op_kind {
+    RY_OP_STEM = 1,       /* 3x3 s2 conv on the fp32 NCHW image + bias + SiLU -> NHWC bf16      (RepS_Block L0)   */
+    RY_OP_CONV = 2,       /* 1x1 / 3x3 (s1,s2) implicit GEMM on tcgen05 + fused epilogue                            */
+    RY_OP_DW5 = 3,        /* depthwise 5x5 s1 + bias + act                                       (GSConv.cv2)      */
+    RY_OP_MAXPOOL2 = 4,   /* 2x2 s2 max-pool                                                     (MP)              */
+    RY_OP_SPP = 5,        /* 5/9/13 s1 max-pools, written at three channel offsets               (SPPCSPC.m)       */
+    RY_OP_UPSAMPLE2 = 6,  /* nearest x2                                                          (nn.Upsample)     */
+    RY_OP_CA = 7,         /* global avg-pool + f1/ReLU + f2/sigmoid, out = p*s + p -> VEC         (CA)              */
+    RY_OP_ATTN_QK = 8,    /* grouped 1x1 q/k convs + SiLU + shared BN + ReLU6 -> fp32 q,k         (attention q/k)   */
+    RY_OP_CRISSCROSS = 9, /* CrissCrossAttention core: gamma*out + x                                                */
+    RY_OP_VERTICAL = 10,  /* VerticalAttention core:   gamma*out + x                                                */
+    RY_OP_DETECT = 11     /* head 1x1 conv on tcgen05 + sigmoid/grid/anchor decode -> pred + raw  (IDetect)         */
+};
+
+enum ry_act { RY_ACT_NONE = 0, RY_ACT_SILU = 1 };
+
+typedef struct ry_op_desc {
+    int32_t kind;          /* ry_op_kind */
+    int32_t layer;         /* top-level reference layer index (models/yolo.py forward_once) this op belongs to */
+    ry_view in0;           /* main input                                                           */
+    ry_view in1;           /* CONV: residual added after act (same shape as out) | attention: q    */
+    ry_view in2;           /* CONV: per-image broadcast vector added after act   | attention: k    */
+    ry_view out0;          /* main output (SPP: the 5x5 pool; ATTN_QK: q)                          */
+    ry_view out1;          /* CONV/DW5 split store: second half of the channels | SPP: 9x9 | ATTN_QK: k */
+    ry_view out2;          /* SPP: 13x13                                                           */
+    int32_t ksize;         /* 1 or 3 (CONV), 3 (STEM), 5 (DW5) */
+    int32_t stride;        /* 1 or 2 */
+    int32_t act;           /* ry_act */
+    int32_t cin, cout;
+    int32_t level_idx;     /* DETECT: pyramid level (row offset / stride / anchors) */
+    int64_t w_off;         /* byte offsets into the host weight blob; -1 = none.                                    */
+    int64_t b_off;         /*   CONV/STEM/DETECT: w = fp32 [cout][cin][k][k] (PyTorch OIHW), b = fp32 [cout]        */
+    int64_t aux_off[6];    /*   DW5: w = fp32 [C][5][5]; CA: w = f1 [C/16][C], aux0 = f2 [C][C/16];                 */
+                           /*   ATTN_QK: w = wq [Cq][8], b = bq, aux0 = wk, aux1 = bk, aux2/3 = shared BN scale/shift*/
+                           /*   CRISSCROSS/VERTICAL: w = wv [C], b = bv [C], aux0/1 = BN1 scale/shift [C]           */
+    float fparam[8];       /* CRISSCROSS/VERTICAL: [0] = gamma;  DETECT: [0] = stride, [1..6] = anchor (w,h) x 3    */
+} ry_op_desc;
+
+/* ---- plan lifetime ------------------------------------------------------------------------------------------- */
+
+int ry_abi_version(void);
+const char *ry_last_error(void);            /* thread-local, valid until the next failing call on this thread */
+
+/* Copies the op list, packs the weights (bf16, UMMA K-major order) into plan-owned device memory on `device`. */
+int ry_plan_create(const ry_tensor_desc *tensors, int n_tensors, const ry_op_desc *ops, int n_ops,
+                   const void *weights_host, size_t weight_bytes, int nc, int device, ry_plan **out);
+void ry_plan_destroy(ry_plan *plan);
+
+/* Bytes of caller-provided workspace (activation arena) for a [B,3,H,W] input; H, W multiples of 32. */
+int ry_plan_workspace_bytes(ry_plan *plan, int B, int H, int W, size_t *bytes);
+/* Lays the tensors out in `workspace`, encodes the TMA descriptors for this shape.  Not a hot call. */
+int ry_plan_bind(ry_plan *plan, int B, int H, int W, void *workspace, size_t workspace_bytes);
+/* Byte offset inside the bound workspace and NHWC dims of tensor `t` (for teacher-forced tests / taps). */
+int ry_plan_tensor_info(ry_plan *plan, int t, size_t *offset, int *h, int *w, int *c, int *dtype);
+int ry_plan_num_candidates(ry_plan *plan, int *n);   /* rows of pred per image for the bound shape (25200 @ 640x640) */
+
+/* ---- hot calls ----------------------------------------------------------------------------------------------- */
+
+/* image: fp32 NCHW [B,3,H,W] in [0,1];  pred: fp32 [B,N,5+nc];  raw0..2: fp32 [B,na,ny,nx,5+nc] (may be NULL). */
+int ry_forward(ry_plan *plan, const float *image, float *pred, float *raw0, float *raw1, float *raw2, void *stream);
+/* Runs ops [first,last) of the bound plan (externals as given; NULL allowed when the range does not touch them). */
+int ry_run_ops(ry_plan *plan, int first, int last, const float *image, float *pred, float *raw0, float *raw1,
+               float *raw2, void *stream);
+/* Number of kernel launches ry_forward issues for the bound shape (for bench.py's gpu_launches). */
+int ry_plan_launch_count(ry_plan *plan, int *n);
+
+/* non_max_suppression.  pred: fp32 [B,N,5+nc] (not modified).  out: fp32 [B,max_det,6] rows (x1,y1,x2,y2,conf,cls)
+ * in score order, counts: int32 [B].  classes: HOST array or NULL.  iou_thres is compared in double like torchvision. */
+int ry_nms_workspace_bytes(int B, int N, int nc, int multi_label, size_t *bytes);
+int ry_nms(const float *pred, int B, int N, int nc, float conf_thres, double iou_thres, const int32_t *classes_host,
+           int n_classes, int agnostic, int multi_label, int max_det, int max_nms, float *out, int32_t *counts,
+           void *workspace, size_t workspace_bytes, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* REPYOLO_B200_H */

@@ -1,0 +1,11 @@
+"""repyolo_b200: B200-native (sm_100a) implementation of Rep-YOLO's deployed inference hot path.
+
+Public surface = the reference's own call signatures for this path:
+    Model(cfg).fuse().forward(x)      (models/yolo.py)      -> (pred [B, N, 5+nc], [raw heads])
+    non_max_suppression(pred, ...)    (utils/general.py)    -> list of (n, 6) tensors
+Everything numerical runs in csrc/librepyolo_b200.so (include/repyolo_b200.h); there is no CPU fallback.
+"""
+from .model import Model, IDetect, NativeEngine          # noqa: F401
+from .nms import non_max_suppression, nms_padded          # noqa: F401
+from ._lib import NativeError, lib                        # noqa: F401
+from .arch import rep_yolo_cfg                            # noqa: F401

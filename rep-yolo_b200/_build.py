@@ -1,0 +1,59 @@
+"""In-tree build of the CUDA library (sm_100a only).  `python -m` friendly: ``python rep-yolo_b200/_build.py``."""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, 'csrc')
+SO = os.path.join(CSRC, 'librepyolo_b200.so')
+SOURCES = ['conv_umma.cu', 'memops.cu', 'attention.cu', 'nms.cu', 'plan.cu']
+NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '-Xcompiler', '-fPIC',
+              '--threads', '4']
+
+
+def _nvcc() -> str:
+    for c in (os.environ.get('NVCC'), '/usr/local/cuda/bin/nvcc', 'nvcc'):
+        if c and (os.path.isabs(c) and os.path.exists(c) or not os.path.isabs(c)):
+            return c
+    raise RuntimeError('nvcc not found')
+
+
+def stale() -> bool:
+    if not os.path.exists(SO):
+        return True
+    t = os.path.getmtime(SO)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.cu', '.cuh'))]
+    deps.append(os.path.join(os.path.dirname(HERE), 'include', 'repyolo_b200.h'))
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile every CUDA source into one shared library next to the sources (objects in csrc/_obj)."""
+    if not force and not stale():
+        return SO
+    obj_dir = os.path.join(CSRC, '_obj')
+    os.makedirs(obj_dir, exist_ok=True)
+    nvcc = _nvcc()
+    procs = []
+    for src in SOURCES:
+        obj = os.path.join(obj_dir, src.replace('.cu', '.o'))
+        cmd = [nvcc, *NVCC_FLAGS, '-c', os.path.join(CSRC, src), '-o', obj]
+        if verbose:
+            cmd.insert(1, '-Xptxas=-v')
+        procs.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    objs = []
+    for src, obj, p in procs:
+        out, _ = p.communicate()
+        if verbose and out:
+            print(out)
+        if p.returncode != 0:
+            raise RuntimeError(f'nvcc failed on {src}:\n{out}')
+        objs.append(obj)
+    subprocess.check_call([nvcc, '-shared', '-o', SO, *objs, '-gencode', 'arch=compute_100a,code=sm_100a'])
+    return SO
+
+
+if __name__ == '__main__':
+    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))

@@ -1,0 +1,53 @@
+// Shared host/device helpers for the repyolo_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <string>
+
+namespace ry {
+
+void set_error(const std::string &msg);   // plan.cu
+
+#define RY_CUDA(expr)                                                                                       \
+    do {                                                                                                    \
+        cudaError_t err__ = (expr);                                                                         \
+        if (err__ != cudaSuccess) {                                                                         \
+            ry::set_error(std::string(#expr) + ": " + cudaGetErrorString(err__) + " (" + __FILE__ + ":" +   \
+                          std::to_string(__LINE__) + ")");                                                  \
+            return 1;                                                                                       \
+        }                                                                                                   \
+    } while (0)
+
+#define RY_FAIL(msg)                        \
+    do {                                    \
+        ry::set_error(std::string(msg));    \
+        return 1;                           \
+    } while (0)
+
+constexpr int kNumSMs = 148;
+
+__host__ __device__ inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float relu6_f(float x) { return fminf(fmaxf(x, 0.0f), 6.0f); }
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t *>(&v);
+}
+__device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
+    __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162 *>(&u);
+    return __bfloat1622float2(v);
+}
+__device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
+    __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162 *>(&a), *reinterpret_cast<__nv_bfloat162 *>(&b));
+    return *reinterpret_cast<uint32_t *>(&r);
+}
+__device__ __forceinline__ uint4 bf16x8_max(uint4 a, uint4 b) {
+    return make_uint4(bf16x2_max(a.x, b.x), bf16x2_max(a.y, b.y), bf16x2_max(a.z, b.z), bf16x2_max(a.w, b.w));
+}
+
+}  // namespace ry

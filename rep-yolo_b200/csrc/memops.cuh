@@ -1,0 +1,43 @@
+// Launchers of the memory-bound kernels (memops.cu) and the attention kernels (attention.cu).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+namespace ry {
+
+int stem_launch(const float *img, const float *w27, const float *bias, __nv_bfloat16 *out, int out_cs, int out_off,
+                int cout, int B, int H, int W, cudaStream_t st);
+void dw5_launch(const __nv_bfloat16 *in, int in_cs, int in_off0, int in_off1, __nv_bfloat16 *out, int out_cs, int out_off0,
+                int out_off1, const float *w, const float *bias, int C, int half, int B, int H, int W, int act,
+                cudaStream_t st);
+void maxpool2_launch(const __nv_bfloat16 *in, int in_cs, int in_off, __nv_bfloat16 *out, int out_cs, int out_off, int C,
+                     int B, int H, int W, cudaStream_t st);
+void spp_launch(const __nv_bfloat16 *in, int in_cs, int in_off, __nv_bfloat16 *out, int out_cs, int off5, int off9,
+                int off13, int C, int B, int H, int W, cudaStream_t st);
+void upsample2_launch(const __nv_bfloat16 *in, int in_cs, int in_off, __nv_bfloat16 *out, int out_cs, int out_off, int C,
+                      int B, int H, int W, cudaStream_t st);
+void ca_launch(const __nv_bfloat16 *in, int in_cs, int in_off, float *out, int out_cs, int out_off, const float *f1,
+               const float *f2, int C, int B, int HW, cudaStream_t st);
+
+// ---- attention (attention.cu) ----
+struct AttnParams {
+    const __nv_bfloat16 *x;   // input map view
+    int x_cs, x_off;
+    int C, Cq;                // Cq = C / 8
+    int B, H, W;
+    const float *q, *k;       // [B, H*W, Cq] fp32 (written by attn_qk_launch)
+    const float *wv, *bv;     // value conv (depthwise 1x1 folded with its BN): v = relu6(s1 * silu(wv*x + bv) + t1)
+    const float *s1, *t1;     // stand-alone BN1 as scale/shift
+    float gamma;
+    __nv_bfloat16 *out;       // output map view
+    int out_cs, out_off;
+    float *scratch;           // criss-cross row pass partials: [B*H*W, C + 2] fp32
+};
+void attn_qk_launch(const __nv_bfloat16 *x, int x_cs, int x_off, int C, int Cq, size_t npix, const float *wq,
+                    const float *bq, const float *wk, const float *bk, const float *s, const float *t, float *q, float *k,
+                    cudaStream_t st);
+int crisscross_launch(const AttnParams &p, cudaStream_t st);
+int vertical_launch(const AttnParams &p, cudaStream_t st);
+size_t crisscross_scratch_floats(int B, int H, int W, int C);
+
+}  // namespace ry

@@ -1,0 +1,407 @@
+// non_max_suppression on the GPU, bit-exact against the reference (utils/general.py:953-1045 + torchvision.ops.nms).
+//
+//   1. nms_filter   : one CTA per image walks the candidates IN ORDER: obj > conf (fp32), conf = obj*cls (nc > 1) or obj
+//                     (nc == 1, general.py:994-998), xywh->xyxy (general.py:265-272, same op order), best-class or
+//                     multi-label rows, class filter; ordered (prefix-sum) compaction -> rows[n][6] + sort keys.
+//   2. radix sort   : stable LSD radix sort (4 x 8 bit) of the keys per image, score descending; stability gives the
+//                     "ties -> lower index first" order of torchvision's stable sort.  hist -> scan -> scatter per pass.
+//   3. nms_scan     : one CTA per image consumes the sorted candidates in chunks of 512: suppress by the boxes kept so
+//                     far, build the 512x512 bit mask of the chunk (class-offset boxes, general.py:1027-1028), resolve
+//                     it with a deterministic serial keep-scan, stop at max_det keeps (exact: general.py:1030-1031
+//                     truncates AFTER nms and greedy decisions only depend on higher-ranked boxes) or after max_nms
+//                     candidates (general.py:1023-1024, stable variant).
+// IoU arithmetic uses explicit round-to-nearest intrinsics (no FMA contraction) and the threshold compare is done in
+// double, exactly like torchvision's CPU kernel.
+#include "nms.cuh"
+
+#include "common.cuh"
+
+namespace ry {
+
+namespace {
+
+constexpr int kFilterThreads = 1024;
+constexpr int kSortThreads = 256;
+constexpr int kSortWarps = kSortThreads / 32;
+constexpr int kSortItems = 16;                           // keys per thread
+constexpr int kSortTile = kSortThreads * kSortItems;     // 4096 keys per CTA
+constexpr int kChunk = 512;                              // sorted candidates per scan step
+constexpr int kChunkWords = kChunk / 64;
+constexpr float kMaxWh = 4096.0f;                        // general.py:965
+
+__device__ __forceinline__ uint32_t desc_key(float s) {
+    uint32_t u = __float_as_uint(s);
+    u ^= (u >> 31) ? 0xFFFFFFFFu : 0x80000000u;          // ascending order-preserving map of all floats
+    return ~u;                                           // descending
+}
+
+// ---- block-wide exclusive scan of one int per thread (blockDim.x <= 1024), returns total in *total ----
+__device__ __forceinline__ int block_excl_scan(int v, int *warp_sums, int *total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) warp_sums[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        int s = lane < nw ? warp_sums[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, s, o);
+            if (lane >= o) s += y;
+        }
+        warp_sums[lane] = s;                             // inclusive over warps
+    }
+    __syncthreads();
+    const int base = warp > 0 ? warp_sums[warp - 1] : 0;
+    *total = warp_sums[nw - 1];
+    __syncthreads();
+    return base + x - v;
+}
+
+__global__ void __launch_bounds__(kFilterThreads) nms_filter_kernel(const float *__restrict__ pred, int N, int nc,
+                                                                    float conf, int multi_label,
+                                                                    const int *__restrict__ classes, int n_classes,
+                                                                    size_t cap, float *__restrict__ rows,
+                                                                    uint32_t *__restrict__ keys, uint32_t *__restrict__ idx,
+                                                                    int *__restrict__ counts) {
+    __shared__ int warp_sums[32];
+    const int b = blockIdx.x, no = 5 + nc;
+    const float *P = pred + (size_t)b * N * no;
+    float *R = rows + (size_t)b * cap * 6;
+    uint32_t *Kb = keys + (size_t)b * cap, *Ib = idx + (size_t)b * cap;
+    int base = 0;
+    for (int i0 = 0; i0 < N; i0 += blockDim.x) {
+        const int i = i0 + threadIdx.x;
+        int cnt = 0;
+        float x1 = 0, y1 = 0, x2 = 0, y2 = 0, obj = 0, best = 0;
+        int bj = 0;
+        const float *p = P + (size_t)i * no;
+        if (i < N) {
+            obj = p[4];
+            if (obj > conf) {                                                  // general.py:962, 978
+                const float cx = p[0], cy = p[1], w = p[2], h = p[3];
+                x1 = __fsub_rn(cx, __fdiv_rn(w, 2.0f));                        // general.py:268-271
+                y1 = __fsub_rn(cy, __fdiv_rn(h, 2.0f));
+                x2 = __fadd_rn(cx, __fdiv_rn(w, 2.0f));
+                y2 = __fadd_rn(cy, __fdiv_rn(h, 2.0f));
+                if (multi_label) {                                             // general.py:1004-1006
+                    for (int j = 0; j < nc; ++j) {
+                        const float c = __fmul_rn(p[5 + j], obj);
+                        bool ok = c > conf;
+                        if (ok && n_classes > 0) {
+                            ok = false;
+                            for (int q = 0; q < n_classes; ++q) ok |= (classes[q] == j);
+                        }
+                        cnt += ok ? 1 : 0;
+                    }
+                } else {                                                       // general.py:1008-1009
+                    for (int j = 0; j < nc; ++j) {
+                        const float c = (nc == 1) ? obj : __fmul_rn(p[5 + j], obj);
+                        if (j == 0 || c > best) { best = c; bj = j; }
+                    }
+                    bool ok = best > conf;
+                    if (ok && n_classes > 0) {                                 // general.py:1012-1013
+                        ok = false;
+                        for (int q = 0; q < n_classes; ++q) ok |= (classes[q] == bj);
+                    }
+                    cnt = ok ? 1 : 0;
+                }
+            }
+        }
+        int total;
+        int off = base + block_excl_scan(cnt, warp_sums, &total);
+        if (cnt > 0) {
+            if (multi_label) {
+                for (int j = 0; j < nc; ++j) {
+                    const float c = __fmul_rn(p[5 + j], obj);
+                    bool ok = c > conf;
+                    if (ok && n_classes > 0) {
+                        ok = false;
+                        for (int q = 0; q < n_classes; ++q) ok |= (classes[q] == j);
+                    }
+                    if (ok) {
+                        float *r = R + (size_t)off * 6;
+                        r[0] = x1; r[1] = y1; r[2] = x2; r[3] = y2; r[4] = c; r[5] = (float)j;
+                        Kb[off] = desc_key(c);
+                        Ib[off] = (uint32_t)off;
+                        ++off;
+                    }
+                }
+            } else {
+                float *r = R + (size_t)off * 6;
+                r[0] = x1; r[1] = y1; r[2] = x2; r[3] = y2; r[4] = best; r[5] = (float)bj;
+                Kb[off] = desc_key(best);
+                Ib[off] = (uint32_t)off;
+            }
+        }
+        base += total;
+    }
+    if (threadIdx.x == 0) counts[b] = base;
+}
+
+// ---- radix sort ----------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kSortThreads) sort_hist_kernel(const uint32_t *__restrict__ keys, const int *__restrict__ counts,
+                                                                 size_t cap, int shift, int nblk, uint32_t *__restrict__ hist) {
+    __shared__ uint32_t h[256];
+    const int b = blockIdx.y, blk = blockIdx.x;
+    const int n = counts[b];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t *K = keys + (size_t)b * cap;
+    const int start = blk * kSortTile;
+    for (int i = start + threadIdx.x; i < min(start + kSortTile, n); i += kSortThreads) atomicAdd(&h[(K[i] >> shift) & 255], 1u);
+    __syncthreads();
+    hist[((size_t)b * 256 + threadIdx.x) * nblk + blk] = h[threadIdx.x];
+}
+
+// exclusive scan of hist[b][digit][blk] in (digit-major, blk-minor) order -> global output offsets
+__global__ void __launch_bounds__(256) sort_scan_kernel(uint32_t *__restrict__ hist, int nblk) {
+    __shared__ int warp_sums[32];
+    const int b = blockIdx.x, d = threadIdx.x;
+    uint32_t *h = hist + ((size_t)b * 256 + d) * nblk;
+    int sum = 0;
+    for (int j = 0; j < nblk; ++j) sum += (int)h[j];
+    int total;
+    int run = block_excl_scan(sum, warp_sums, &total);
+    for (int j = 0; j < nblk; ++j) {
+        const int c = (int)h[j];
+        h[j] = (uint32_t)run;
+        run += c;
+    }
+}
+
+__global__ void __launch_bounds__(kSortThreads) sort_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ idx_in,
+                                                                    uint32_t *__restrict__ keys_out, uint32_t *__restrict__ idx_out,
+                                                                    const int *__restrict__ counts, size_t cap, int shift, int nblk,
+                                                                    const uint32_t *__restrict__ hist) {
+    __shared__ uint32_t cnt[kSortWarps][256];
+    const int b = blockIdx.y, blk = blockIdx.x;
+    const int n = counts[b];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < kSortWarps * 256; i += kSortThreads) (&cnt[0][0])[i] = 0;
+    __syncthreads();
+    const uint32_t *K = keys_in + (size_t)b * cap, *I = idx_in + (size_t)b * cap;
+    const int wstart = blk * kSortTile + warp * (32 * kSortItems);   // each warp owns a contiguous run of the tile
+    uint32_t key[kSortItems], val[kSortItems], rank[kSortItems];
+#pragma unroll
+    for (int r = 0; r < kSortItems; ++r) {
+        const int i = wstart + r * 32 + lane;
+        const bool valid = i < n;
+        const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+        rank[r] = 0;
+        if (valid) {
+            key[r] = K[i];
+            val[r] = I[i];
+            const uint32_t d = (key[r] >> shift) & 255;
+            const uint32_t peers = __match_any_sync(vmask, d);
+            const uint32_t prior = cnt[warp][d];
+            __syncwarp(vmask);
+            if ((peers & ((1u << lane) - 1)) == 0) cnt[warp][d] = prior + __popc(peers);   // lowest lane of the group
+            __syncwarp(vmask);
+            rank[r] = prior + __popc(peers & ((1u << lane) - 1));
+        }
+    }
+    __syncthreads();
+    {   // per digit: exclusive prefix over warps + global base of this (image, digit, block)
+        const int d = threadIdx.x;
+        uint32_t run = hist[((size_t)b * 256 + d) * nblk + blk];
+#pragma unroll
+        for (int w = 0; w < kSortWarps; ++w) {
+            const uint32_t c = cnt[w][d];
+            cnt[w][d] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+    uint32_t *Ko = keys_out + (size_t)b * cap, *Io = idx_out + (size_t)b * cap;
+#pragma unroll
+    for (int r = 0; r < kSortItems; ++r) {
+        const int i = wstart + r * 32 + lane;
+        if (i < n) {
+            const uint32_t pos = cnt[warp][(key[r] >> shift) & 255] + rank[r];
+            Ko[pos] = key[r];
+            Io[pos] = val[r];
+        }
+    }
+}
+
+// ---- greedy scan ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool iou_gt(float ax1, float ay1, float ax2, float ay2, float aa, float bx1, float by1, float bx2,
+                                       float by2, float ba, double thr) {
+    const float xx1 = fmaxf(ax1, bx1), yy1 = fmaxf(ay1, by1), xx2 = fminf(ax2, bx2), yy2 = fminf(ay2, by2);
+    const float w = fmaxf(__fsub_rn(xx2, xx1), 0.0f), h = fmaxf(__fsub_rn(yy2, yy1), 0.0f);
+    const float inter = __fmul_rn(w, h);
+    const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(aa, ba), inter));
+    return (double)ovr > thr;
+}
+
+__global__ void __launch_bounds__(kChunk) nms_scan_kernel(const float *__restrict__ rows, const uint32_t *__restrict__ order,
+                                                          const int *__restrict__ counts, size_t cap, double iou_thr,
+                                                          int agnostic, int max_det, int max_nms, float *__restrict__ out,
+                                                          int *__restrict__ out_counts) {
+    extern __shared__ unsigned char smraw[];
+    // chunk boxes (SoA) | mask | kept boxes (SoA) | control
+    float *cx1 = reinterpret_cast<float *>(smraw), *cy1 = cx1 + kChunk, *cx2 = cy1 + kChunk, *cy2 = cx2 + kChunk, *car = cy2 + kChunk;
+    unsigned long long *mask = reinterpret_cast<unsigned long long *>(car + kChunk);       // [kChunk][kChunkWords]
+    unsigned long long *dead = mask + (size_t)kChunk * kChunkWords;                          // [kChunkWords]
+    float *kx1 = reinterpret_cast<float *>(dead + kChunkWords), *ky1 = kx1 + max_det, *kx2 = ky1 + max_det, *ky2 = kx2 + max_det,
+          *kar = ky2 + max_det;
+    int *ctl = reinterpret_cast<int *>(kar + max_det);                                       // [0] kept so far, [1] kept before chunk
+    int *newkeep = ctl + 2;                                                                  // [kChunk] chunk-local indices kept
+
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int n = min(counts[b], max_nms);
+    const float *R = rows + (size_t)b * cap * 6;
+    const uint32_t *O = order + (size_t)b * cap;
+    float *outb = out + (size_t)b * max_det * 6;
+    if (tid == 0) { ctl[0] = 0; ctl[1] = 0; }
+    __syncthreads();
+
+    for (int c0 = 0; c0 < n; c0 += kChunk) {
+        const int cs = min(kChunk, n - c0);
+        const int kept0 = ctl[0];
+        if (kept0 >= max_det) break;
+        // ---- load my box (class offset added in fp32 BEFORE the IoU, general.py:1027-1028) ----
+        uint32_t ridx = 0;
+        bool is_dead = true;
+        float x1 = 0, y1 = 0, x2 = 0, y2 = 0, ar = 0;
+        if (tid < cs) {
+            ridx = O[c0 + tid];
+            const float *r = R + (size_t)ridx * 6;
+            const float off = agnostic ? __fmul_rn(r[5], 0.0f) : __fmul_rn(r[5], kMaxWh);
+            x1 = __fadd_rn(r[0], off); y1 = __fadd_rn(r[1], off); x2 = __fadd_rn(r[2], off); y2 = __fadd_rn(r[3], off);
+            ar = __fmul_rn(__fsub_rn(x2, x1), __fsub_rn(y2, y1));
+            cx1[tid] = x1; cy1[tid] = y1; cx2[tid] = x2; cy2[tid] = y2; car[tid] = ar;
+            is_dead = false;
+            for (int k = 0; k < kept0; ++k)                                   // suppressed by an earlier keep?
+                if (iou_gt(kx1[k], ky1[k], kx2[k], ky2[k], kar[k], x1, y1, x2, y2, ar, iou_thr)) { is_dead = true; break; }
+        }
+        const uint32_t dm = __ballot_sync(0xffffffffu, is_dead);
+        if ((tid & 31) == 0) reinterpret_cast<uint32_t *>(dead)[tid >> 5] = dm;
+        __syncthreads();
+        // ---- chunk mask: mask[i][w] bit j = box i suppresses box (64w + j), only j > i matters ----
+        for (int e = tid; e < cs * kChunkWords; e += kChunk) {
+            const int i = e / kChunkWords, w = e - i * kChunkWords;
+            unsigned long long bits = 0;
+            const bool i_dead = (dead[i >> 6] >> (i & 63)) & 1ull;
+            if (!i_dead && 64 * w + 63 > i) {
+                const float ax1 = cx1[i], ay1 = cy1[i], ax2 = cx2[i], ay2 = cy2[i], aa = car[i];
+                const int j0 = max(64 * w, i + 1), j1 = min(64 * w + 64, cs);
+                for (int j = j0; j < j1; ++j)
+                    if (iou_gt(ax1, ay1, ax2, ay2, aa, cx1[j], cy1[j], cx2[j], cy2[j], car[j], iou_thr)) bits |= 1ull << (j & 63);
+            }
+            mask[(size_t)i * kChunkWords + w] = bits;
+        }
+        __syncthreads();
+        // ---- deterministic serial keep-scan (one thread; <= kChunk steps, early exit at max_det) ----
+        if (tid == 0) {
+            int kept = kept0, nk = 0;
+            for (int w = 0; w < kChunkWords && kept < max_det; ++w) {
+                while (kept < max_det) {
+                    const unsigned long long avail = ~dead[w];        // bits >= cs are dead from the load phase
+                    if (!avail) break;
+                    const int bit = __ffsll((long long)avail) - 1, i = 64 * w + bit;
+                    newkeep[nk++] = i;
+                    ++kept;
+                    dead[w] |= 1ull << bit;                            // consumed
+                    const unsigned long long *m = mask + (size_t)i * kChunkWords;
+                    for (int w2 = w; w2 < kChunkWords; ++w2) dead[w2] |= m[w2];
+                }
+            }
+            ctl[1] = kept0;
+            ctl[0] = kept;
+        }
+        __syncthreads();
+        // ---- publish the new keeps: kept-box list (for later chunks) and output rows (un-offset boxes, general.py:1040) ----
+        const int nk = ctl[0] - kept0;
+        for (int t = tid; t < nk; t += kChunk) {
+            const int i = newkeep[t], slot = kept0 + t;
+            kx1[slot] = cx1[i]; ky1[slot] = cy1[i]; kx2[slot] = cx2[i]; ky2[slot] = cy2[i]; kar[slot] = car[i];
+            const float *r = R + (size_t)O[c0 + i] * 6;
+            float *o = outb + (size_t)slot * 6;
+#pragma unroll
+            for (int q = 0; q < 6; ++q) o[q] = r[q];
+        }
+        __syncthreads();
+    }
+    if (tid == 0) out_counts[b] = ctl[0];
+}
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct NmsLayout {
+    size_t cap, rows, keys0, keys1, idx0, idx1, counts, hist, classes, total;
+    int nblk;
+};
+
+NmsLayout nms_layout(int B, int N, int nc, int multi_label) {
+    NmsLayout L;
+    L.cap = (size_t)N * ((multi_label && nc > 1) ? nc : 1);
+    L.nblk = (int)((L.cap + kSortTile - 1) / kSortTile);
+    size_t o = 0;
+    L.rows = o;    o = align_up(o + (size_t)B * L.cap * 6 * 4, 256);
+    L.keys0 = o;   o = align_up(o + (size_t)B * L.cap * 4, 256);
+    L.keys1 = o;   o = align_up(o + (size_t)B * L.cap * 4, 256);
+    L.idx0 = o;    o = align_up(o + (size_t)B * L.cap * 4, 256);
+    L.idx1 = o;    o = align_up(o + (size_t)B * L.cap * 4, 256);
+    L.counts = o;  o = align_up(o + (size_t)B * 4, 256);
+    L.hist = o;    o = align_up(o + (size_t)B * 256 * L.nblk * 4, 256);
+    L.classes = o; o = align_up(o + 1024 * 4, 256);
+    L.total = o;
+    return L;
+}
+
+}  // namespace
+
+size_t nms_workspace_bytes(int B, int N, int nc, int multi_label) { return nms_layout(B, N, nc, multi_label).total; }
+
+int nms_launch_count(int B, int N, int nc, int multi_label) {
+    (void)B; (void)N; (void)nc; (void)multi_label;
+    return 1 + 4 * 3 + 1;
+}
+
+int nms_run(const float *pred, int B, int N, int nc, float conf, double iou, const int32_t *classes_host, int n_classes,
+            int agnostic, int multi_label, int max_det, int max_nms, float *out, int32_t *counts, void *workspace,
+            size_t workspace_bytes, cudaStream_t st) {
+    multi_label = (multi_label && nc > 1) ? 1 : 0;                                         // general.py:970
+    const NmsLayout L = nms_layout(B, N, nc, multi_label);
+    if (workspace_bytes < L.total) RY_FAIL("ry_nms: workspace too small");
+    if (n_classes > 1024) RY_FAIL("ry_nms: more than 1024 classes in the filter list");
+    if (max_det < 1 || max_det > 4096) RY_FAIL("ry_nms: max_det out of range");
+    if (B <= 0 || N <= 0) RY_FAIL("ry_nms: empty input");
+    unsigned char *ws = static_cast<unsigned char *>(workspace);
+    float *rows = reinterpret_cast<float *>(ws + L.rows);
+    uint32_t *k0 = reinterpret_cast<uint32_t *>(ws + L.keys0), *k1 = reinterpret_cast<uint32_t *>(ws + L.keys1);
+    uint32_t *i0 = reinterpret_cast<uint32_t *>(ws + L.idx0), *i1 = reinterpret_cast<uint32_t *>(ws + L.idx1);
+    int *cnt = reinterpret_cast<int *>(ws + L.counts);
+    uint32_t *hist = reinterpret_cast<uint32_t *>(ws + L.hist);
+    int *cls = reinterpret_cast<int *>(ws + L.classes);
+    if (n_classes > 0) RY_CUDA(cudaMemcpyAsync(cls, classes_host, (size_t)n_classes * 4, cudaMemcpyHostToDevice, st));
+
+    nms_filter_kernel<<<B, kFilterThreads, 0, st>>>(pred, N, nc, conf, multi_label, cls, n_classes, L.cap, rows, k0, i0, cnt);
+    const dim3 sgrid(L.nblk, B);
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 8 * pass;
+        sort_hist_kernel<<<sgrid, kSortThreads, 0, st>>>(k0, cnt, L.cap, shift, L.nblk, hist);
+        sort_scan_kernel<<<B, 256, 0, st>>>(hist, L.nblk);
+        sort_scatter_kernel<<<sgrid, kSortThreads, 0, st>>>(k0, i0, k1, i1, cnt, L.cap, shift, L.nblk, hist);
+        uint32_t *t = k0; k0 = k1; k1 = t;
+        t = i0; i0 = i1; i1 = t;
+    }
+    const size_t smem = (size_t)5 * kChunk * 4 + (size_t)kChunk * kChunkWords * 8 + kChunkWords * 8 + (size_t)5 * max_det * 4 +
+                        2 * 4 + (size_t)kChunk * 4;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr_set = true;
+    }
+    nms_scan_kernel<<<B, kChunk, smem, st>>>(rows, i0, cnt, L.cap, iou, agnostic, max_det, max_nms, out, counts);
+    RY_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace ry

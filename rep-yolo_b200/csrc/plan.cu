@@ -1,0 +1,605 @@
+// Plan / executor and the C ABI (include/repyolo_b200.h).
+//
+// A plan is the fused deploy graph of the reference's Model.fuse() + forward_once (models/yolo.py:569-619, 681-704) as a
+// flat op list over NHWC bf16 tensors.  ry_plan_create packs the weights once (bf16, K-major, padded to the UMMA K block);
+// ry_plan_bind lays the tensors out in the caller's workspace and encodes the TMA descriptors for one input shape;
+// ry_forward / ry_run_ops only launch kernels on the caller's stream.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/repyolo_b200.h"
+#include "common.cuh"
+#include "conv_umma.cuh"
+#include "memops.cuh"
+#include "nms.cuh"
+
+namespace ry {
+
+static thread_local std::string g_error;
+void set_error(const std::string &msg) { g_error = msg; }
+
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct Tensor {
+    ry_tensor_desc d;
+    size_t offset = 0, bytes = 0;
+    int h = 0, w = 0;
+};
+
+struct ConvPacked {          // shape-independent part of a CONV / DETECT op
+    int kb = 0, cblk = 0, ntaps = 0, BN = 0, n_ntiles = 0, k_pad = 0, cout_pad = 0;
+    size_t w_dev = 0, b_dev = 0;   // byte offsets in the device weight buffer
+};
+
+struct Op {
+    ry_op_desc d;
+    ConvPacked cp;
+    size_t dev[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // device weight-buffer offsets of the op's parameter arrays
+    // shape-dependent (filled by bind)
+    ConvArgs ca;
+    int grid = 0;
+    int tmap_first = -1;
+    int launches = 0;
+};
+
+}  // namespace
+}  // namespace ry
+
+struct ry_plan {
+    int device = 0, nc = 1;
+    std::vector<ry::Tensor> tensors;
+    std::vector<ry::Op> ops;
+    unsigned char *d_weights = nullptr;
+    size_t weight_bytes = 0;
+    // bound state
+    int B = 0, H = 0, W = 0;
+    unsigned char *ws = nullptr;
+    size_t ws_bytes = 0, scratch_off = 0;
+    CUtensorMap *d_tmaps = nullptr;
+    size_t tmaps_cap = 0;
+    int n_cand = 0;
+};
+
+namespace ry {
+namespace {
+
+struct Blob {                 // host staging of the device weight buffer
+    std::vector<unsigned char> data;
+    size_t add(const void *src, size_t bytes) {
+        const size_t off = align_up(data.size(), 256);
+        data.resize(off + bytes);
+        if (src) memcpy(data.data() + off, src, bytes);
+        return off;
+    }
+};
+
+int pack_conv(const ry_op_desc &d, const unsigned char *host, size_t host_bytes, Blob &blob, ConvPacked &cp) {
+    const int cin = d.cin, cout = d.cout, k = d.ksize;
+    if (k != 1 && k != 3) RY_FAIL("conv: ksize must be 1 or 3");
+    if (cin % 8 != 0) RY_FAIL("conv: cin must be a multiple of 8");
+    if (d.w_off < 0 || d.b_off < 0 || (size_t)d.w_off + (size_t)cout * cin * k * k * 4 > host_bytes ||
+        (size_t)d.b_off + (size_t)cout * 4 > host_bytes)
+        RY_FAIL("conv: weight offsets out of range");
+    cp.kb = (cin % 64 == 0) ? 64 : (cin % 32 == 0 ? 32 : 16);
+    cp.cblk = (cin + cp.kb - 1) / cp.kb;
+    cp.ntaps = k * k;
+    cp.k_pad = cp.ntaps * cp.cblk * cp.kb;
+    const int c16 = (cout + 15) / 16 * 16;
+    cp.BN = c16 <= 256 ? c16 : 256;
+    if (c16 > 256 && c16 % 256 != 0) cp.BN = 128;
+    cp.n_ntiles = (c16 + cp.BN - 1) / cp.BN;
+    cp.cout_pad = cp.n_ntiles * cp.BN;
+    const float *w = reinterpret_cast<const float *>(host + d.w_off);
+    const float *b = reinterpret_cast<const float *>(host + d.b_off);
+    std::vector<__nv_bfloat16> wp((size_t)cp.cout_pad * cp.k_pad, __float2bfloat16(0.0f));
+    for (int co = 0; co < cout; ++co)
+        for (int ci = 0; ci < cin; ++ci)
+            for (int t = 0; t < cp.ntaps; ++t)
+                wp[(size_t)co * cp.k_pad + (size_t)t * cp.cblk * cp.kb + ci] =
+                    __float2bfloat16_rn(w[((size_t)co * cin + ci) * cp.ntaps + t]);
+    std::vector<float> bp(cp.cout_pad, 0.0f);
+    for (int co = 0; co < cout; ++co) bp[co] = b[co];
+    cp.w_dev = blob.add(wp.data(), wp.size() * sizeof(__nv_bfloat16));
+    cp.b_dev = blob.add(bp.data(), bp.size() * sizeof(float));
+    return 0;
+}
+
+int copy_f32(const unsigned char *host, size_t host_bytes, int64_t off, size_t n, Blob &blob, size_t *dev) {
+    if (off < 0 || (size_t)off + n * 4 > host_bytes) RY_FAIL("weight offset out of range");
+    *dev = blob.add(host + off, n * 4);
+    return 0;
+}
+
+void pick_tile(int B, int Ho, int Wo, int *tw, int *th, int *tn) {
+    long best_tiles = -1;
+    int bw = 1, bh = 1, bn = 1;
+    for (int w = std::min(Wo, 128); w >= 1; --w) {
+        for (int h = std::min(Ho, 128 / w); h >= 1; --h) {
+            const int n = std::max(1, std::min(B, 128 / (w * h)));
+            const long tiles = (long)cdiv(Wo, w) * cdiv(Ho, h) * cdiv(B, n);
+            if (best_tiles < 0 || tiles < best_tiles) { best_tiles = tiles; bw = w; bh = h; bn = n; }
+        }
+    }
+    *tw = bw; *th = bh; *tn = bn;
+}
+
+int encode_map(CUtensorMap *m, void *base, int rank, const cuuint64_t *dims, const cuuint64_t *strides_bytes,
+               const cuuint32_t *box, int kb) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) RY_FAIL("cuTensorMapEncodeTiled entry point not available (driver too old?)");
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    const CUtensorMapSwizzle sw = kb == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (kb == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+    const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, base, dims, strides_bytes, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) RY_FAIL("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+    return 0;
+}
+
+int view_ok(const ry_plan *p, const ry_view &v, bool required) {
+    if (v.tensor < 0) return required ? 1 : 0;
+    if (v.tensor >= (int)p->tensors.size()) return 1;
+    const Tensor &t = p->tensors[v.tensor];
+    if (t.d.kind == RY_T_EXTERNAL) return 0;
+    if (v.c_off < 0 || v.c_len <= 0 || v.c_off + v.c_len > t.d.channels || v.c_off % 8 != 0) return 1;
+    return 0;
+}
+
+inline __nv_bfloat16 *bf(ry_plan *p, int t) { return reinterpret_cast<__nv_bfloat16 *>(p->ws + p->tensors[t].offset); }
+inline float *f32(ry_plan *p, int t) { return reinterpret_cast<float *>(p->ws + p->tensors[t].offset); }
+inline const float *wf(ry_plan *p, size_t off) { return reinterpret_cast<const float *>(p->d_weights + off); }
+
+// Fill the shape-dependent ConvArgs + tensor maps of one CONV / DETECT op.
+int bind_conv(ry_plan *p, Op &op, std::vector<CUtensorMap> &maps) {
+    const ry_op_desc &d = op.d;
+    const ConvPacked &cp = op.cp;
+    const Tensor &tin = p->tensors[d.in0.tensor];
+    const int s = d.stride, k = d.ksize;
+    const int Hi = tin.h, Wi = tin.w, Ho = Hi / s, Wo = Wi / s, B = p->B;
+    if (s != 1 && !(s == 2 && k == 3)) RY_FAIL("conv: only 1x1 s1, 3x3 s1 and 3x3 s2 are built");
+    ConvArgs &a = op.ca;
+    memset(&a, 0, sizeof(a));
+    a.kb = cp.kb; a.cblk = cp.cblk; a.ntaps = cp.ntaps; a.kblocks = cp.ntaps * cp.cblk;
+    a.BN = cp.BN; a.n_ntiles = cp.n_ntiles;
+    a.stages = conv_pick_stages(cp.BN);
+    a.img_w = Wo; a.img_hw = Ho * Wo;
+    op.tmap_first = (int)maps.size();
+    const size_t esz = 2;
+    const cuuint64_t ctot = (cuuint64_t)tin.d.channels;
+    __nv_bfloat16 *in_base = bf(p, d.in0.tensor) + d.in0.c_off;
+    CUtensorMap m;
+    if (k == 1) {
+        const cuuint64_t P = (cuuint64_t)B * Hi * Wi;
+        a.tw = 128; a.th = 1; a.tn = 1;
+        a.Wo = (int)P; a.Ho = 1; a.Bo = 1;
+        const cuuint64_t dims[4] = {(cuuint64_t)d.cin, P, 1, 1};
+        const cuuint64_t str[3] = {ctot * esz, P * ctot * esz, P * ctot * esz};
+        const cuuint32_t box[4] = {(cuuint32_t)cp.kb, 128, 1, 1};
+        if (encode_map(&m, in_base, 4, dims, str, box, cp.kb)) return 1;
+        maps.push_back(m);
+        a.tap_map[0] = 0; a.tap_dh[0] = 0; a.tap_dw[0] = 0;
+    } else {
+        pick_tile(B, Ho, Wo, &a.tw, &a.th, &a.tn);
+        a.Wo = Wo; a.Ho = Ho; a.Bo = B;
+        const cuuint32_t box[4] = {(cuuint32_t)cp.kb, (cuuint32_t)a.tw, (cuuint32_t)a.th, (cuuint32_t)a.tn};
+        if (s == 1) {
+            const cuuint64_t dims[4] = {(cuuint64_t)d.cin, (cuuint64_t)Wi, (cuuint64_t)Hi, (cuuint64_t)B};
+            const cuuint64_t str[3] = {ctot * esz, (cuuint64_t)Wi * ctot * esz, (cuuint64_t)Hi * Wi * ctot * esz};
+            if (encode_map(&m, in_base, 4, dims, str, box, cp.kb)) return 1;
+            maps.push_back(m);
+            for (int t = 0; t < 9; ++t) { a.tap_map[t] = 0; a.tap_dh[t] = (int8_t)(t / 3 - 1); a.tap_dw[t] = (int8_t)(t % 3 - 1); }
+        } else {
+            // stride 2: the four parity phases of the input are unit-stride tensors with doubled pitches
+            for (int ph = 0; ph < 2; ++ph)
+                for (int pw = 0; pw < 2; ++pw) {
+                    const cuuint64_t dims[4] = {(cuuint64_t)d.cin, (cuuint64_t)((Wi - pw + 1) / 2), (cuuint64_t)((Hi - ph + 1) / 2),
+                                                (cuuint64_t)B};
+                    const cuuint64_t str[3] = {2 * ctot * esz, 2 * (cuuint64_t)Wi * ctot * esz, (cuuint64_t)Hi * Wi * ctot * esz};
+                    if (encode_map(&m, in_base + ((size_t)ph * Wi + pw) * ctot, 4, dims, str, box, cp.kb)) return 1;
+                    maps.push_back(m);
+                }
+            for (int t = 0; t < 9; ++t) {
+                const int kh = t / 3, kw = t % 3;
+                const int ph = kh == 1 ? 0 : 1, pw = kw == 1 ? 0 : 1;
+                a.tap_map[t] = (int8_t)(ph * 2 + pw);
+                a.tap_dh[t] = (int8_t)(kh == 0 ? -1 : 0);
+                a.tap_dw[t] = (int8_t)(kw == 0 ? -1 : 0);
+            }
+        }
+    }
+    a.tiles_w = cdiv(a.Wo, a.tw); a.tiles_h = cdiv(a.Ho, a.th); a.tiles_n = cdiv(a.Bo, a.tn);
+    {   // weights: [cout_pad][k_pad]
+        const cuuint64_t dims[2] = {(cuuint64_t)cp.k_pad, (cuuint64_t)cp.cout_pad};
+        const cuuint64_t str[1] = {(cuuint64_t)cp.k_pad * esz};
+        const cuuint32_t box[2] = {(cuuint32_t)cp.kb, (cuuint32_t)cp.BN};
+        if (encode_map(&m, p->d_weights + cp.w_dev, 2, dims, str, box, cp.kb)) return 1;
+        maps.push_back(m);
+    }
+    a.bias = wf(p, cp.b_dev);
+    a.cout = d.cout;
+    a.act = d.act;
+    const long tiles = (long)a.tiles_w * a.tiles_h * a.tiles_n * a.n_ntiles;
+    op.grid = (int)std::min<long>(tiles, kNumSMs);
+    op.launches = 1;
+    if (d.kind == RY_OP_DETECT) {
+        a.mode = 1;
+        a.no = p->nc + 5;
+        a.na = d.cout / a.no;
+        a.det_stride = d.fparam[0];
+        for (int i = 0; i < 6; ++i) a.anchors[i] = d.fparam[1 + i];
+        a.split_at = 1 << 30;
+        return 0;
+    }
+    a.mode = 0;
+    const Tensor &tout = p->tensors[d.out0.tensor];
+    if (tout.h != Ho || tout.w != Wo) RY_FAIL("conv: output tensor level does not match stride");
+    a.out = bf(p, d.out0.tensor);
+    a.out_cs = tout.d.channels;
+    a.off0 = d.out0.c_off;
+    if (d.out1.tensor >= 0) {
+        if (d.out1.tensor != d.out0.tensor || d.out0.c_len % 16 != 0) RY_FAIL("conv: bad split store");
+        a.split_at = d.out0.c_len;
+        a.off1 = d.out1.c_off;
+    } else {
+        a.split_at = 1 << 30;
+    }
+    if (d.in1.tensor >= 0) {
+        a.res = bf(p, d.in1.tensor);
+        a.res_cs = p->tensors[d.in1.tensor].d.channels;
+        a.res_off = d.in1.c_off;
+    }
+    if (d.in2.tensor >= 0) {
+        a.bvec = f32(p, d.in2.tensor);
+        a.bvec_cs = p->tensors[d.in2.tensor].d.channels;
+        a.bvec_off = d.in2.c_off;
+    }
+    return 0;
+}
+
+int run_op(ry_plan *p, Op &op, const float *image, float *pred, float *raws[3], cudaStream_t st) {
+    const ry_op_desc &d = op.d;
+    const int B = p->B;
+    switch (d.kind) {
+        case RY_OP_STEM: {
+            if (!image) RY_FAIL("stem: image pointer is NULL");
+            const Tensor &to = p->tensors[d.out0.tensor];
+            if (stem_launch(image, wf(p, op.dev[0]), wf(p, op.dev[1]), bf(p, d.out0.tensor), to.d.channels, d.out0.c_off, d.cout, B,
+                            p->H, p->W, st))
+                RY_FAIL("stem: unsupported cout");
+            break;
+        }
+        case RY_OP_CONV: {
+            ConvArgs a = op.ca;
+            a.amap = p->d_tmaps + op.tmap_first;
+            a.wmap = p->d_tmaps + op.tmap_first + (d.stride == 2 ? 4 : 1);
+            conv_launch(a, op.grid, st);
+            break;
+        }
+        case RY_OP_DETECT: {
+            if (!pred) RY_FAIL("detect: pred pointer is NULL");
+            ConvArgs a = op.ca;
+            a.amap = p->d_tmaps + op.tmap_first;
+            a.wmap = p->d_tmaps + op.tmap_first + 1;
+            a.pred = pred;
+            a.raw = raws[d.level_idx];
+            conv_launch(a, op.grid, st);
+            break;
+        }
+        case RY_OP_DW5: {
+            const Tensor &ti = p->tensors[d.in0.tensor], &to = p->tensors[d.out0.tensor];
+            const int C = d.cin;
+            const bool split = d.in1.tensor >= 0;
+            const int half = split ? d.in0.c_len : C;
+            dw5_launch(bf(p, d.in0.tensor), ti.d.channels, d.in0.c_off, split ? d.in1.c_off : 0, bf(p, d.out0.tensor),
+                       to.d.channels, d.out0.c_off, split ? d.out1.c_off : 0, wf(p, op.dev[0]), wf(p, op.dev[1]), C, half, B,
+                       ti.h, ti.w, d.act, st);
+            break;
+        }
+        case RY_OP_MAXPOOL2: {
+            const Tensor &ti = p->tensors[d.in0.tensor], &to = p->tensors[d.out0.tensor];
+            maxpool2_launch(bf(p, d.in0.tensor), ti.d.channels, d.in0.c_off, bf(p, d.out0.tensor), to.d.channels, d.out0.c_off,
+                            d.in0.c_len, B, ti.h, ti.w, st);
+            break;
+        }
+        case RY_OP_SPP: {
+            const Tensor &ti = p->tensors[d.in0.tensor], &to = p->tensors[d.out0.tensor];
+            spp_launch(bf(p, d.in0.tensor), ti.d.channels, d.in0.c_off, bf(p, d.out0.tensor), to.d.channels, d.out0.c_off,
+                       d.out1.c_off, d.out2.c_off, d.in0.c_len, B, ti.h, ti.w, st);
+            break;
+        }
+        case RY_OP_UPSAMPLE2: {
+            const Tensor &ti = p->tensors[d.in0.tensor], &to = p->tensors[d.out0.tensor];
+            upsample2_launch(bf(p, d.in0.tensor), ti.d.channels, d.in0.c_off, bf(p, d.out0.tensor), to.d.channels, d.out0.c_off,
+                             d.in0.c_len, B, ti.h, ti.w, st);
+            break;
+        }
+        case RY_OP_CA: {
+            const Tensor &ti = p->tensors[d.in0.tensor], &to = p->tensors[d.out0.tensor];
+            ca_launch(bf(p, d.in0.tensor), ti.d.channels, d.in0.c_off, f32(p, d.out0.tensor), to.d.channels, d.out0.c_off,
+                      wf(p, op.dev[0]), wf(p, op.dev[1]), d.in0.c_len, B, ti.h * ti.w, st);
+            break;
+        }
+        case RY_OP_ATTN_QK: {
+            const Tensor &ti = p->tensors[d.in0.tensor];
+            attn_qk_launch(bf(p, d.in0.tensor), ti.d.channels, d.in0.c_off, d.cin, d.cout, (size_t)B * ti.h * ti.w, wf(p, op.dev[0]),
+                           wf(p, op.dev[1]), wf(p, op.dev[2]), wf(p, op.dev[3]), wf(p, op.dev[4]), wf(p, op.dev[5]),
+                           f32(p, d.out0.tensor), f32(p, d.out1.tensor), st);
+            break;
+        }
+        case RY_OP_CRISSCROSS:
+        case RY_OP_VERTICAL: {
+            const Tensor &ti = p->tensors[d.in0.tensor], &to = p->tensors[d.out0.tensor];
+            AttnParams ap;
+            ap.x = bf(p, d.in0.tensor); ap.x_cs = ti.d.channels; ap.x_off = d.in0.c_off;
+            ap.C = d.cin; ap.Cq = d.cin / 8; ap.B = B; ap.H = ti.h; ap.W = ti.w;
+            ap.q = f32(p, d.in1.tensor); ap.k = f32(p, d.in2.tensor);
+            ap.wv = wf(p, op.dev[0]); ap.bv = wf(p, op.dev[1]); ap.s1 = wf(p, op.dev[2]); ap.t1 = wf(p, op.dev[3]);
+            ap.gamma = d.fparam[0];
+            ap.out = bf(p, d.out0.tensor); ap.out_cs = to.d.channels; ap.out_off = d.out0.c_off;
+            ap.scratch = reinterpret_cast<float *>(p->ws + p->scratch_off);
+            const int rc = d.kind == RY_OP_CRISSCROSS ? crisscross_launch(ap, st) : vertical_launch(ap, st);
+            if (rc == 2) RY_FAIL("VerticalAttention with H != W is not built yet (reference view-chain semantics, SURVEY 8 a19)");
+            if (rc) RY_FAIL("attention: unsupported shape (shared memory)");
+            break;
+        }
+        default: RY_FAIL("unknown op kind");
+    }
+    return 0;
+}
+
+size_t tensor_bytes(const Tensor &t, int B, int H, int W) {
+    const size_t e = t.d.dtype == RY_BF16 ? 2 : 4;
+    if (t.d.kind == RY_T_MAP) return (size_t)B * (H >> t.d.level) * (W >> t.d.level) * t.d.channels * e;
+    if (t.d.kind == RY_T_VEC) return (size_t)B * t.d.channels * e;
+    return 0;
+}
+
+size_t scratch_bytes(const ry_plan *p, int B, int H, int W) {
+    size_t m = 0;
+    for (const Op &op : p->ops)
+        if (op.d.kind == RY_OP_CRISSCROSS) {
+            const Tensor &t = p->tensors[op.d.in0.tensor];
+            m = std::max(m, crisscross_scratch_floats(B, H >> t.d.level, W >> t.d.level, op.d.cin) * 4);
+        }
+    return m;
+}
+
+}  // namespace
+}  // namespace ry
+
+using namespace ry;
+
+extern "C" {
+
+int ry_abi_version(void) { return RY_ABI_VERSION; }
+const char *ry_last_error(void) { return g_error.c_str(); }
+
+int ry_plan_create(const ry_tensor_desc *tensors, int n_tensors, const ry_op_desc *ops, int n_ops, const void *weights_host,
+                   size_t weight_bytes, int nc, int device, ry_plan **out) {
+    if (!tensors || !ops || !out || n_tensors <= 0 || n_ops <= 0) RY_FAIL("ry_plan_create: bad arguments");
+    RY_CUDA(cudaSetDevice(device));
+    ry_plan *p = new ry_plan();
+    p->device = device;
+    p->nc = nc;
+    p->tensors.resize(n_tensors);
+    for (int i = 0; i < n_tensors; ++i) p->tensors[i].d = tensors[i];
+    p->ops.resize(n_ops);
+    const unsigned char *host = static_cast<const unsigned char *>(weights_host);
+    Blob blob;
+    int rc = 0;
+    for (int i = 0; i < n_ops && !rc; ++i) {
+        Op &op = p->ops[i];
+        op.d = ops[i];
+        const ry_op_desc &d = op.d;
+        const ry_view *vs[6] = {&d.in0, &d.in1, &d.in2, &d.out0, &d.out1, &d.out2};
+        for (int v = 0; v < 6; ++v)
+            if (view_ok(p, *vs[v], v == 0 || v == 3)) { set_error("op " + std::to_string(i) + ": bad tensor view"); rc = 1; }
+        if (rc) break;
+        switch (d.kind) {
+            case RY_OP_CONV:
+            case RY_OP_DETECT: rc = pack_conv(d, host, weight_bytes, blob, op.cp); break;
+            case RY_OP_STEM: {
+                if (d.cin != 3 || d.ksize != 3 || d.stride != 2) { set_error("stem: expects 3x3 s2 on 3 channels"); rc = 1; break; }
+                if (d.w_off < 0 || (size_t)d.w_off + (size_t)d.cout * 27 * 4 > weight_bytes) { set_error("stem: weight offset"); rc = 1; break; }
+                const float *w = reinterpret_cast<const float *>(host + d.w_off);
+                std::vector<float> w27((size_t)27 * d.cout);
+                for (int co = 0; co < d.cout; ++co)
+                    for (int t = 0; t < 27; ++t) w27[(size_t)t * d.cout + co] = w[(size_t)co * 27 + t];
+                op.dev[0] = blob.add(w27.data(), w27.size() * 4);
+                rc = copy_f32(host, weight_bytes, d.b_off, d.cout, blob, &op.dev[1]);
+                break;
+            }
+            case RY_OP_DW5: {
+                const int C = d.cin;
+                if (d.w_off < 0 || (size_t)d.w_off + (size_t)C * 25 * 4 > weight_bytes) { set_error("dw5: weight offset"); rc = 1; break; }
+                const float *w = reinterpret_cast<const float *>(host + d.w_off);
+                std::vector<float> wt((size_t)25 * C);
+                for (int c = 0; c < C; ++c)
+                    for (int t = 0; t < 25; ++t) wt[(size_t)t * C + c] = w[(size_t)c * 25 + t];
+                op.dev[0] = blob.add(wt.data(), wt.size() * 4);
+                rc = copy_f32(host, weight_bytes, d.b_off, C, blob, &op.dev[1]);
+                break;
+            }
+            case RY_OP_CA: {
+                const int C = d.cin;
+                rc = copy_f32(host, weight_bytes, d.w_off, (size_t)(C / 16) * C, blob, &op.dev[0]) ||
+                     copy_f32(host, weight_bytes, d.aux_off[0], (size_t)C * (C / 16), blob, &op.dev[1]);
+                break;
+            }
+            case RY_OP_ATTN_QK: {
+                const int Cq = d.cout;
+                rc = copy_f32(host, weight_bytes, d.w_off, (size_t)Cq * 8, blob, &op.dev[0]) ||
+                     copy_f32(host, weight_bytes, d.b_off, Cq, blob, &op.dev[1]) ||
+                     copy_f32(host, weight_bytes, d.aux_off[0], (size_t)Cq * 8, blob, &op.dev[2]) ||
+                     copy_f32(host, weight_bytes, d.aux_off[1], Cq, blob, &op.dev[3]) ||
+                     copy_f32(host, weight_bytes, d.aux_off[2], Cq, blob, &op.dev[4]) ||
+                     copy_f32(host, weight_bytes, d.aux_off[3], Cq, blob, &op.dev[5]);
+                break;
+            }
+            case RY_OP_CRISSCROSS:
+            case RY_OP_VERTICAL: {
+                const int C = d.cin;
+                rc = copy_f32(host, weight_bytes, d.w_off, C, blob, &op.dev[0]) || copy_f32(host, weight_bytes, d.b_off, C, blob, &op.dev[1]) ||
+                     copy_f32(host, weight_bytes, d.aux_off[0], C, blob, &op.dev[2]) ||
+                     copy_f32(host, weight_bytes, d.aux_off[1], C, blob, &op.dev[3]);
+                break;
+            }
+            default: break;
+        }
+    }
+    if (rc) { delete p; return 1; }
+    p->weight_bytes = std::max<size_t>(blob.data.size(), 256);
+    if (cudaMalloc(&p->d_weights, p->weight_bytes) != cudaSuccess) { delete p; RY_FAIL("cudaMalloc of the weight buffer failed"); }
+    if (cudaMemcpy(p->d_weights, blob.data.data(), blob.data.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaFree(p->d_weights);
+        delete p;
+        RY_FAIL("weight upload failed");
+    }
+    *out = p;
+    return 0;
+}
+
+void ry_plan_destroy(ry_plan *p) {
+    if (!p) return;
+    if (p->d_weights) cudaFree(p->d_weights);
+    if (p->d_tmaps) cudaFree(p->d_tmaps);
+    delete p;
+}
+
+int ry_plan_workspace_bytes(ry_plan *p, int B, int H, int W, size_t *bytes) {
+    if (!p || !bytes || B <= 0 || H <= 0 || W <= 0 || H % 32 || W % 32) RY_FAIL("workspace_bytes: H and W must be positive multiples of 32");
+    size_t total = 0;
+    for (const Tensor &t : p->tensors) total += align_up(tensor_bytes(t, B, H, W), 1024);
+    total += align_up(scratch_bytes(p, B, H, W), 1024);
+    *bytes = total + 1024;
+    return 0;
+}
+
+int ry_plan_bind(ry_plan *p, int B, int H, int W, void *workspace, size_t workspace_bytes) {
+    size_t need = 0;
+    if (ry_plan_workspace_bytes(p, B, H, W, &need)) return 1;
+    if (!workspace || workspace_bytes < need) RY_FAIL("bind: workspace too small");
+    RY_CUDA(cudaSetDevice(p->device));
+    p->B = B; p->H = H; p->W = W;
+    unsigned char *base = reinterpret_cast<unsigned char *>(align_up(reinterpret_cast<size_t>(workspace), 1024));
+    p->ws = base;
+    p->ws_bytes = workspace_bytes - (size_t)(base - static_cast<unsigned char *>(workspace));
+    size_t off = 0;
+    for (Tensor &t : p->tensors) {
+        t.h = t.d.kind == RY_T_MAP ? (H >> t.d.level) : 1;
+        t.w = t.d.kind == RY_T_MAP ? (W >> t.d.level) : 1;
+        t.bytes = tensor_bytes(t, B, H, W);
+        t.offset = off;
+        off += align_up(t.bytes, 1024);
+    }
+    p->scratch_off = off;
+    std::vector<CUtensorMap> maps;
+    p->n_cand = 0;
+    for (Op &op : p->ops) {
+        op.launches = 1;
+        if (op.d.kind == RY_OP_CONV || op.d.kind == RY_OP_DETECT) {
+            if (bind_conv(p, op, maps)) return 1;
+        }
+        if (op.d.kind == RY_OP_CRISSCROSS) op.launches = 2;
+    }
+    // Detect rows: level -> anchor -> y -> x (models/yolo.py:152, 166)
+    int rows = 0;
+    for (Op &op : p->ops)
+        if (op.d.kind == RY_OP_DETECT) {
+            op.ca.row_off = rows;
+            rows += op.ca.na * op.ca.img_hw;
+        }
+    for (Op &op : p->ops)
+        if (op.d.kind == RY_OP_DETECT) op.ca.rows_total = rows;
+    p->n_cand = rows;
+    if (maps.size() > p->tmaps_cap) {
+        if (p->d_tmaps) cudaFree(p->d_tmaps);
+        p->d_tmaps = nullptr;
+        RY_CUDA(cudaMalloc(&p->d_tmaps, maps.size() * sizeof(CUtensorMap)));
+        p->tmaps_cap = maps.size();
+    }
+    if (!maps.empty()) RY_CUDA(cudaMemcpy(p->d_tmaps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int ry_plan_tensor_info(ry_plan *p, int t, size_t *offset, int *h, int *w, int *c, int *dtype) {
+    if (!p || t < 0 || t >= (int)p->tensors.size() || !p->ws) RY_FAIL("tensor_info: bad tensor or plan not bound");
+    const Tensor &T = p->tensors[t];
+    if (offset) *offset = T.offset;
+    if (h) *h = T.h;
+    if (w) *w = T.w;
+    if (c) *c = T.d.channels;
+    if (dtype) *dtype = T.d.dtype;
+    return 0;
+}
+
+int ry_plan_num_candidates(ry_plan *p, int *n) {
+    if (!p || !p->ws || !n) RY_FAIL("num_candidates: plan not bound");
+    *n = p->n_cand;
+    return 0;
+}
+
+int ry_plan_launch_count(ry_plan *p, int *n) {
+    if (!p || !p->ws || !n) RY_FAIL("launch_count: plan not bound");
+    int c = 0;
+    for (const Op &op : p->ops) c += op.launches;
+    *n = c;
+    return 0;
+}
+
+int ry_run_ops(ry_plan *p, int first, int last, const float *image, float *pred, float *raw0, float *raw1, float *raw2,
+               void *stream) {
+    if (!p || !p->ws) RY_FAIL("run_ops: plan not bound");
+    if (first < 0 || last > (int)p->ops.size() || first > last) RY_FAIL("run_ops: bad op range");
+    float *raws[3] = {raw0, raw1, raw2};
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    for (int i = first; i < last; ++i)
+        if (run_op(p, p->ops[i], image, pred, raws, st)) return 1;
+    RY_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int ry_forward(ry_plan *p, const float *image, float *pred, float *raw0, float *raw1, float *raw2, void *stream) {
+    if (!p) RY_FAIL("forward: NULL plan");
+    return ry_run_ops(p, 0, (int)p->ops.size(), image, pred, raw0, raw1, raw2, stream);
+}
+
+int ry_nms_workspace_bytes(int B, int N, int nc, int multi_label, size_t *bytes) {
+    if (!bytes || B <= 0 || N <= 0 || nc <= 0) RY_FAIL("nms_workspace_bytes: bad arguments");
+    *bytes = nms_workspace_bytes(B, N, nc, multi_label);
+    return 0;
+}
+
+int ry_nms(const float *pred, int B, int N, int nc, float conf_thres, double iou_thres, const int32_t *classes_host,
+           int n_classes, int agnostic, int multi_label, int max_det, int max_nms, float *out, int32_t *counts, void *workspace,
+           size_t workspace_bytes, void *stream) {
+    if (!pred || !out || !counts || !workspace) RY_FAIL("ry_nms: NULL pointer");
+    return nms_run(pred, B, N, nc, conf_thres, iou_thres, classes_host, n_classes, agnostic, multi_label, max_det, max_nms, out,
+                   counts, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

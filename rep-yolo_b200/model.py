@@ -1,0 +1,247 @@
+"""Host-side mirror of the reference ``models.yolo.Model`` / ``IDetect`` for the deployed path.
+
+Keeps the call signatures the reference's detect.py / test.py use:
+    Model(cfg, ch, nc, anchors)  .fuse() -> self   .forward(x, augment=False, profile=False) -> (pred, [raw0, raw1, raw2])
+    model.model[-1] : detect layer with .stride .nl .na .no .nc .anchors .anchor_grid and .fuseforward(list_of_maps)
+    model.stride, model.names, model.yaml, model.save
+Parameters carry the reference checkpoint's state_dict names, so ``load_state_dict(reference_model.state_dict())`` works.
+Only the fused (deploy) forward exists, and it runs in the CUDA library -- there is no PyTorch fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import torch
+import torch.nn as nn
+
+from . import _lib as N
+from . import arch, fold, planner
+
+
+class _Node(nn.Module):
+    """Generic container used to reproduce the reference's dotted parameter names."""
+
+    def __getitem__(self, i):
+        return getattr(self, str(i if i >= 0 else len(self._modules) + i))
+
+    def __len__(self):
+        return len(self._modules)
+
+
+def _insert(root, name, tensor, is_buffer):
+    *path, leaf = name.split('.')
+    node = root
+    for part in path:
+        if part not in node._modules:
+            node.add_module(part, _Node())
+        node = node._modules[part]
+    if is_buffer:
+        node.register_buffer(leaf, tensor)
+    else:
+        node.register_parameter(leaf, nn.Parameter(tensor, requires_grad=False))
+
+
+class NativeEngine:
+    """One bound plan per input shape, on one device."""
+
+    def __init__(self, plan_ir, nc, device):
+        self.device = torch.device(device)
+        if self.device.type != 'cuda':
+            raise N.NativeError('the native engine needs a CUDA device (no CPU fallback on this path)')
+        self.nc = nc
+        self.plan_ir = plan_ir
+        P = self.plan_ir
+        self._tensors = (N.TensorDesc * len(P.tensors))(*P.tensors)
+        self._ops = (N.OpDesc * len(P.ops))(*P.ops)
+        blob = P.blob.bytes()
+        handle = C.c_void_p()
+        with torch.cuda.device(self.device):
+            N.check(N.lib().ry_plan_create(self._tensors, len(P.tensors), self._ops, len(P.ops), blob.ctypes.data, blob.nbytes, nc,
+                                           self.device.index or 0, C.byref(handle)), 'ry_plan_create')
+        self.handle = handle
+        self.shape = None
+        self.workspace = None
+        self.n_cand = 0
+
+    def __del__(self):
+        try:
+            if getattr(self, 'handle', None):
+                N.lib().ry_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def bind(self, B, H, W):
+        if self.shape == (B, H, W):
+            return
+        if H % 32 or W % 32:
+            raise ValueError(f'image size {H}x{W} must be a multiple of the max stride 32 (reference check_img_size)')
+        nbytes = C.c_size_t()
+        L = N.lib()
+        N.check(L.ry_plan_workspace_bytes(self.handle, B, H, W, C.byref(nbytes)), 'ry_plan_workspace_bytes')
+        if self.workspace is None or self.workspace.numel() < nbytes.value:
+            self.workspace = None
+            self.workspace = torch.zeros(nbytes.value, dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            torch.cuda.current_stream(self.device).synchronize()
+            N.check(L.ry_plan_bind(self.handle, B, H, W, self.workspace.data_ptr(), self.workspace.numel()), 'ry_plan_bind')
+        n = C.c_int()
+        N.check(L.ry_plan_num_candidates(self.handle, C.byref(n)), 'ry_plan_num_candidates')
+        self.n_cand, self.shape = n.value, (B, H, W)
+
+    def launch_count(self):
+        n = C.c_int()
+        N.check(N.lib().ry_plan_launch_count(self.handle, C.byref(n)), 'ry_plan_launch_count')
+        return n.value
+
+    def tensor(self, t):
+        """torch view of plan tensor ``t`` inside the bound workspace: [B, h, w, C] (maps) or [B, C] (vectors)."""
+        off, h, w, c, dt = C.c_size_t(), C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        N.check(N.lib().ry_plan_tensor_info(self.handle, t, C.byref(off), C.byref(h), C.byref(w), C.byref(c), C.byref(dt)),
+                'ry_plan_tensor_info')
+        dtype = torch.bfloat16 if dt.value == N.RY_BF16 else torch.float32
+        esz = 2 if dt.value == N.RY_BF16 else 4
+        B = self.shape[0]
+        base = (-self.workspace.data_ptr()) % 1024 + off.value
+        kind = self.plan_ir.tensors[t].kind
+        shape = (B, h.value, w.value, c.value) if kind == N.T_MAP else (B, c.value)
+        numel = math.prod(shape)
+        return self.workspace[base:base + numel * esz].view(dtype).view(shape)
+
+    def _outputs(self, B, H, W):
+        no = self.nc + 5
+        pred = torch.empty((B, self.n_cand, no), dtype=torch.float32, device=self.device)
+        raws = [torch.empty((B, 3, H >> l, W >> l, no), dtype=torch.float32, device=self.device) for l in (3, 4, 5)]
+        return pred, raws
+
+    def forward(self, x):
+        B, _, H, W = x.shape
+        self.bind(B, H, W)
+        pred, raws = self._outputs(B, H, W)
+        with torch.cuda.device(self.device):
+            st = torch.cuda.current_stream(self.device).cuda_stream
+            N.check(N.lib().ry_forward(self.handle, x.data_ptr(), pred.data_ptr(), raws[0].data_ptr(), raws[1].data_ptr(),
+                                       raws[2].data_ptr(), C.c_void_p(st)), 'ry_forward')
+        return pred, raws
+
+    def run_ops(self, first, last, image=None, pred=None, raws=(None, None, None)):
+        ptr = lambda t: t.data_ptr() if t is not None else None
+        with torch.cuda.device(self.device):
+            st = torch.cuda.current_stream(self.device).cuda_stream
+            N.check(N.lib().ry_run_ops(self.handle, first, last, ptr(image), ptr(pred), ptr(raws[0]), ptr(raws[1]), ptr(raws[2]),
+                                       C.c_void_p(st)), 'ry_run_ops')
+
+
+class IDetect(_Node):
+    """Detect-layer facade (reference models/yolo.py:93-199): attributes + fuseforward on the native head."""
+    export = False
+    end2end = False
+    include_nms = False
+
+    def _configure(self, owner, nc, anchors, ch):
+        object.__setattr__(self, '_owner', owner)
+        self.nc, self.no, self.nl, self.na = nc, nc + 5, len(anchors), len(anchors[0]) // 2
+        self.stride = torch.tensor(arch.STRIDES)
+        self.f, self.i, self.type = [62, 63, 64], 65, 'models.yolo.IDetect'
+
+    def fuseforward(self, x):
+        """x: list of nl NCHW feature maps.  Mutates the list in place like the reference (yolo.py:140-142)."""
+        return self._owner._detect_only(x)
+
+    forward = fuseforward
+
+
+class Model(nn.Module):
+    def __init__(self, cfg=None, ch=3, nc=None, anchors=None):
+        super().__init__()
+        self.traced = False
+        if cfg is None:
+            cfg = arch.rep_yolo_cfg()
+        if not isinstance(cfg, dict):
+            import yaml
+            with open(cfg) as f:
+                cfg = yaml.safe_load(f)
+        self.yaml = cfg = dict(cfg)
+        cfg['ch'] = cfg.get('ch', ch)
+        if nc and nc != cfg['nc']:
+            cfg['nc'] = nc
+        if anchors:
+            cfg['anchors'] = anchors
+        self._layers, self.save = arch.parse(cfg, cfg['ch'])
+        self.names = [str(i) for i in range(cfg['nc'])]
+        self.model = _Node()
+        det = self._layers[-1]
+        for L in self._layers:                         # one node per reference layer, so model[i] / model[-1] index alike
+            self.model.add_module(str(L.i), IDetect() if L.kind == 'IDetect' else _Node())
+        g = torch.Generator().manual_seed(0)
+        for name, shape in arch.state_shapes(self._layers).items():
+            leaf = name.rsplit('.', 1)[-1]
+            is_buf = leaf in ('running_mean', 'running_var', 'num_batches_tracked', 'anchors', 'anchor_grid')
+            if leaf == 'num_batches_tracked':
+                t = torch.zeros((), dtype=torch.long)
+            elif leaf == 'running_var' or (leaf == 'weight' and len(shape) == 1):
+                t = torch.ones(shape)
+            elif leaf == 'anchor_grid':
+                t = torch.tensor(cfg['anchors'], dtype=torch.float32).view(shape)
+            elif leaf == 'anchors':
+                t = torch.tensor(cfg['anchors'], dtype=torch.float32).view(shape) / torch.tensor(arch.STRIDES).view(-1, 1, 1)
+            elif len(shape) == 4 and leaf == 'weight':
+                bound = 1.0 / math.sqrt(shape[1] * shape[2] * shape[3])
+                t = torch.empty(shape).uniform_(-bound, bound, generator=g)
+            elif leaf == 'implicit':
+                t = torch.empty(shape).normal_(0.0, 0.02, generator=g)
+            else:
+                t = torch.zeros(shape)
+            _insert(self.model, name[len('model.'):], t, is_buf)
+        self.model[-1]._configure(self, cfg['nc'], cfg['anchors'], det.c1)
+        self.stride = self.model[-1].stride
+        self._fused = None
+        self._engine = None
+
+    # ---- reference API ----
+    def fuse(self):
+        """Reference Model.fuse (models/yolo.py:681-704): fold RepConv / RepS_Block / Conv+BN / IDetect implicit layers."""
+        if self._fused is None:
+            with torch.no_grad():
+                self._fused = fold.fold_state_dict(self.state_dict(), self._layers)
+            self._engine = None
+        return self
+
+    def forward(self, x, augment=False, profile=False):
+        if augment:
+            raise NotImplementedError('test-time augmentation (models/yolo.py:570-585) is not built yet')
+        if self._fused is None:
+            raise RuntimeError('only the deployed path is built: call .fuse() first (attempt_load does)')
+        if not x.is_cuda:
+            raise N.NativeError('Model.forward: input must be a CUDA tensor (no CPU fallback on this path)')
+        if x.dtype != torch.float32 or not x.is_contiguous():
+            x = x.float().contiguous()
+        return self.engine(x.device).forward(x)
+
+    def info(self, verbose=False, img_size=640):
+        n_p = sum(p.numel() for p in self.parameters())
+        print(f'Model Summary: {len(self._layers)} layers, {n_p} parameters (native B200 deploy path)')
+
+    # ---- native plumbing ----
+    def engine(self, device):
+        if self._engine is None or self._engine.device != torch.device(device):
+            self._engine = NativeEngine(planner.lower(self._layers, self._fused, self.yaml['nc']), self.yaml['nc'], device)
+        return self._engine
+
+    def _detect_only(self, xs):
+        eng = self.engine(xs[0].device)
+        B, H, W = xs[0].shape[0], xs[0].shape[2] * 8, xs[0].shape[3] * 8
+        eng.bind(B, H, W)
+        grp = eng.plan_ir.groups[-1]
+        for (_, view), x in zip(grp.inputs, xs):
+            t = eng.tensor(view[0])
+            t[..., view[1]:view[1] + view[2]] = x.permute(0, 2, 3, 1).to(torch.bfloat16)
+        pred, raws = eng._outputs(B, H, W)
+        eng.run_ops(grp.first_op, grp.last_op, pred=pred, raws=raws)
+        for i in range(len(xs)):
+            xs[i] = raws[i]
+        det = self.model[-1]
+        if det.end2end:
+            return pred
+        return (pred, xs)

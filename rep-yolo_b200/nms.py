@@ -1,0 +1,66 @@
+"""``non_max_suppression`` with the reference signature (utils/general.py:953), executed by the CUDA library."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib as N
+
+MAX_DET = 300      # utils/general.py:966
+MAX_NMS = 30000    # utils/general.py:967
+_ws_cache = {}
+
+
+def _workspace(device, B, n, nc, multi_label):
+    key = (device, B, n, nc, multi_label)
+    ws = _ws_cache.get(key)
+    if ws is None:
+        nbytes = C.c_size_t()
+        N.check(N.lib().ry_nms_workspace_bytes(B, n, nc, int(multi_label), C.byref(nbytes)), 'ry_nms_workspace_bytes')
+        if len(_ws_cache) > 8:
+            _ws_cache.clear()
+        ws = torch.empty(nbytes.value, dtype=torch.uint8, device=device)
+        _ws_cache[key] = ws
+    return ws
+
+
+def nms_padded(prediction, conf_thres=0.25, iou_thres=0.45, classes=None, agnostic=False, multi_label=False,
+               max_det=MAX_DET, max_nms=MAX_NMS):
+    """Device-side result without any host sync: (out [B, max_det, 6] fp32, counts [B] int32)."""
+    if not prediction.is_cuda:
+        raise N.NativeError('non_max_suppression: prediction must be a CUDA tensor (no CPU fallback on this path)')
+    p = prediction.detach()
+    if p.dtype != torch.float32 or not p.is_contiguous():
+        p = p.float().contiguous()
+    B, n, no = p.shape
+    nc = no - 5
+    multi_label = bool(multi_label) and nc > 1
+    out = torch.empty((B, max_det, 6), dtype=torch.float32, device=p.device)
+    counts = torch.zeros((B,), dtype=torch.int32, device=p.device)
+    if B == 0 or n == 0:
+        return out, counts
+    ws = _workspace(p.device, B, n, nc, multi_label)
+    cls = np.ascontiguousarray(np.asarray(classes if classes is not None else [], dtype=np.int32).reshape(-1))
+    with torch.cuda.device(p.device):
+        st = torch.cuda.current_stream(p.device).cuda_stream
+        N.check(N.lib().ry_nms(p.data_ptr(), B, n, nc, C.c_float(float(np.float32(conf_thres))), C.c_double(float(iou_thres)),
+                               cls.ctypes.data if cls.size else None, int(cls.size), int(bool(agnostic)), int(multi_label),
+                               int(max_det), int(max_nms), out.data_ptr(), counts.data_ptr(), ws.data_ptr(), ws.numel(),
+                               C.c_void_p(st)), 'ry_nms')
+    return out, counts
+
+
+def non_max_suppression(prediction, conf_thres=0.25, iou_thres=0.45, classes=None, agnostic=False, multi_label=False,
+                        labels=()):
+    """Runs NMS on inference results; returns a list of (n, 6) tensors [xyxy, conf, cls] per image, like the reference.
+
+    Differences from the reference, by design: no 10 s ``time_limit`` break, and the > 30000-row cut is the stable one.
+    ``labels`` (test.py --save-hybrid autolabelling) is outside the deployed path and rejected.
+    """
+    if labels is not None and len(labels):
+        raise NotImplementedError('apriori labels (save_hybrid) are not part of the deployed hot path')
+    out, counts = nms_padded(prediction, conf_thres, iou_thres, classes, agnostic, multi_label)
+    cnt = counts.cpu().tolist()                       # the one device->host read of this call
+    return [out[i, :c] for i, c in enumerate(cnt)]

@@ -1,0 +1,76 @@
+"""-m gpu: the tcgen05 implicit-GEMM conv kernel (through ry_plan_* / ry_run_ops) vs torch fp32 conv2d on the same
+bf16-rounded operands.  Tolerance: bf16 output rounding (2^-8 relative) + fp32 accumulation-order noise."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    # cin, cout, k, s, H, W, B, act, kwargs
+    (64, 64, 1, 1, 32, 32, 2, True, {}),
+    (128, 256, 1, 1, 32, 32, 2, True, {}),
+    (64, 64, 3, 1, 32, 32, 2, True, {}),
+    (128, 128, 3, 1, 64, 64, 1, False, {}),
+    (48, 48, 3, 1, 32, 32, 2, True, {}),                 # 16-channel K blocks (32 B swizzle)
+    (24, 24, 3, 1, 32, 32, 2, True, {}),                 # K block padded by TMA zero fill
+    (48, 24, 1, 1, 32, 32, 2, True, {}),
+    (144, 48, 1, 1, 64, 64, 1, True, {}),
+    (32, 64, 1, 1, 32, 32, 1, True, {}),                 # 32-channel K blocks (64 B swizzle)
+    (96, 32, 3, 1, 32, 32, 1, True, {}),
+    (512, 512, 3, 1, 32, 32, 2, True, {}),               # two N tiles, many K blocks
+    (256, 1024, 1, 1, 32, 32, 1, True, {}),              # four N tiles
+    (128, 64, 3, 2, 64, 64, 2, True, {}),                # stride 2 through the parity-phase tensor maps
+    (64, 32, 3, 2, 32, 64, 1, True, {}),
+    (128, 64, 3, 1, 32, 32, 2, True, dict(c_pad_in=64, c_pad_out=32)),      # channel-offset views (concat slots)
+    (128, 128, 1, 1, 32, 32, 2, False, dict(with_res=True)),                # residual epilogue (GSBottleneck shortcut)
+    (128, 128, 1, 1, 32, 32, 2, True, dict(with_bvec=True)),                # broadcast add (CA + CCVA)
+    (128, 64, 1, 1, 32, 32, 2, True, dict(split=True)),                     # split store (GSConv shuffle)
+    (256, 128, 3, 1, 32, 96, 1, True, {}),                                  # non-square, partial tiles
+    (512, 256, 1, 1, 640 // 32 * 32, 640 // 32 * 32, 1, True, {}),           # large M (persistent loop, TMEM double buffer)
+]
+
+
+@pytest.mark.parametrize('case', CASES, ids=lambda c: 'x'.join(str(v) for v in c[:7]))
+def test_conv_vs_torch(case):
+    from gpu_util import single_conv_engine, nchw_to_arena, arena_to_nchw
+    cin, cout, k, s, H, W, B, act, kw = case
+    g = torch.Generator().manual_seed(cin * 131 + cout * 7 + k + s)
+    w = torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5
+    b = torch.randn(cout, generator=g) * 0.5
+    x = torch.randn(B, cin, H, W, generator=g)
+    eng, vin, dst, dst2, res, bvec = single_conv_engine(w, b, B, H, W, s, act, **kw)
+    for t in range(len(eng.plan_ir.tensors)):
+        eng.tensor(t).fill_(7.0)                      # poison: untouched channels must stay untouched
+    nchw_to_arena(eng, vin, x)
+    xb, wb = x.bfloat16().float(), w.bfloat16().float()
+    ref = F.conv2d(xb, wb, b, s, k // 2)
+    if act:
+        ref = F.silu(ref)
+    if res is not None:
+        r = torch.randn(ref.shape, generator=g)
+        nchw_to_arena(eng, res, r)
+        ref = ref + r.bfloat16().float()
+    if bvec is not None:
+        v = torch.randn(B, cout, 1, 1, generator=g)
+        nchw_to_arena(eng, bvec, v)
+        ref = ref + v
+    eng.run_ops(0, 1)
+    torch.cuda.synchronize()
+    if dst2 is None:
+        got = arena_to_nchw(eng, dst)
+    else:
+        got = torch.cat([arena_to_nchw(eng, dst), arena_to_nchw(eng, dst2)], 1)
+    err = (got - ref).abs()
+    tol = 2e-2 + 1e-2 * ref.abs()
+    assert bool((err <= tol).all()), f'max err {err.max().item():.4f} at ref {ref.flatten()[err.argmax()].item():.4f}'
+    rel = float((got - ref).norm() / ref.norm())
+    assert rel < 4e-3, rel
+    # channels outside the destination view are untouched
+    full = eng.tensor(dst[0]).float().cpu()
+    mask = torch.ones(full.shape[-1], dtype=torch.bool)
+    mask[dst[1]:dst[1] + dst[2]] = False
+    if dst2 is not None:
+        mask[dst2[1]:dst2[1] + dst2[2]] = False
+    if mask.any():
+        assert bool((full[..., mask] == 7.0).all())

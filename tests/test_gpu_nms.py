@@ -1,0 +1,104 @@
+"""-m gpu: ry_nms (through the Python mirror of non_max_suppression) must be BIT-EXACT vs the CPU oracle / reference."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from oracle import nms_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _same(a_list, b_list, tag):
+    assert len(a_list) == len(b_list)
+    for i, (a, b) in enumerate(zip(a_list, b_list)):
+        a = a.cpu().numpy()
+        b = b.cpu().numpy()
+        assert a.shape == b.shape, (tag, i, a.shape, b.shape)
+        assert a.tobytes() == b.tobytes(), (tag, i)
+
+
+def test_golden_reference_outputs():
+    import repyolo_b200 as R
+    g = np.load(os.path.join(GOLDEN, 'nms_cases.npz'))
+    meta = json.loads(bytes(g['meta']).decode())
+    for name, kw in meta.items():
+        pred = torch.from_numpy(g[f'{name}.pred']).cuda()
+        outs = R.non_max_suppression(pred, **kw)
+        counts = g[f'{name}.counts']
+        assert [o.shape[0] for o in outs] == counts.tolist(), name
+        got = torch.cat(outs, 0).cpu().numpy()
+        assert got.tobytes() == g[f'{name}.out'].tobytes(), name
+
+
+def _synthetic(B, N, nc, seed, tie=False, span=640.0):
+    g = torch.Generator().manual_seed(seed)
+    cxy = torch.rand(B, N, 2, generator=g) * span
+    wh = torch.exp(torch.empty(B, N, 2).uniform_(np.log(8.0), np.log(320.0), generator=g))
+    obj = torch.rand(B, N, 1, generator=g)
+    cls = torch.rand(B, N, nc, generator=g)
+    if tie:
+        obj = (obj * 20).round() / 20
+        cxy = (cxy / 16).round() * 16
+        wh = (wh / 16).round() * 16 + 16
+    return torch.cat([cxy, wh, obj, cls], 2)
+
+
+@pytest.mark.parametrize('N,nc,conf,iou,ml,tie', [
+    (25200, 1, 0.25, 0.45, False, False),      # detect.py settings at the 640x640 candidate count
+    (25200, 1, 0.001, 0.65, True, False),      # test.py settings (config 5 of BASELINE.json)
+    (25200, 1, 0.001, 0.65, True, True),       # tie-heavy variant (scores quantised to 1/20)
+    (6000, 4, 0.1, 0.6, True, False),          # multi-label
+    (6000, 4, 0.25, 0.45, False, True),
+    (5000, 1, 0.5, 0.5, False, False),
+    (1, 1, 0.25, 0.45, False, False),
+])
+def test_synthetic_vs_oracle(N, nc, conf, iou, ml, tie):
+    import repyolo_b200 as R
+    pred = _synthetic(3, N, nc, seed=N + nc, tie=tie)
+    ref = nms_oracle.non_max_suppression(pred, conf, iou, multi_label=ml)
+    got = R.non_max_suppression(pred.cuda(), conf, iou, multi_label=ml)
+    _same(got, ref, (N, nc, conf, iou, ml, tie))
+
+
+def test_over_max_nms_multilabel():
+    import repyolo_b200 as R
+    pred = _synthetic(2, 4000, 20, seed=9)     # up to 80000 rows per image > max_nms = 30000
+    ref = nms_oracle.non_max_suppression(pred, 0.001, 0.65, multi_label=True)
+    got = R.non_max_suppression(pred.cuda(), 0.001, 0.65, multi_label=True)
+    _same(got, ref, 'over_max_nms')
+
+
+def test_agnostic_classes_empty():
+    import repyolo_b200 as R
+    pred = _synthetic(2, 3000, 4, seed=4)
+    pred[1, :, 4] = 0.0                        # image 1 has no candidate -> (0, 6)
+    for kw in (dict(agnostic=True), dict(classes=[1, 3]), dict(classes=[2], agnostic=True)):
+        ref = nms_oracle.non_max_suppression(pred, 0.25, 0.45, **kw)
+        got = R.non_max_suppression(pred.cuda(), 0.25, 0.45, **kw)
+        _same(got, ref, kw)
+        assert got[1].shape == (0, 6)
+
+
+def test_full_size_properties():
+    """BASELINE config 5 size (256 x 25200): size-independent properties + oracle check on a sample of images."""
+    import repyolo_b200 as R
+    pred = _synthetic(256, 25200, 1, seed=0)
+    dets = R.non_max_suppression(pred.cuda(), 0.001, 0.65, multi_label=True)
+    assert len(dets) == 256
+    for d in dets:
+        d = d.cpu()
+        assert d.shape[0] <= 300 and d.shape[1] == 6
+        assert bool((d[1:, 4] <= d[:-1, 4]).all())                      # sorted by confidence
+        assert bool((d[:, 2] >= d[:, 0]).all() and (d[:, 3] >= d[:, 1]).all())
+    idx = [0, 17, 100, 255]
+    ref = nms_oracle.non_max_suppression(pred[idx], 0.001, 0.65, multi_label=True)
+    _same([dets[i] for i in idx], ref, 'config5 sample')
+    # idempotence: NMS of its own survivors (as cx,cy,w,h rows) keeps them all
+    d = dets[0]
+    rows = torch.stack([(d[:, 0] + d[:, 2]) / 2, (d[:, 1] + d[:, 3]) / 2, d[:, 2] - d[:, 0], d[:, 3] - d[:, 1], d[:, 4], d[:, 4]], 1)
+    again = R.non_max_suppression(rows[None].contiguous(), 0.001, 0.65)
+    assert again[0].shape[0] >= d.shape[0] - 2                          # re-derived xyxy can move by an ulp
