@@ -99,6 +99,7 @@ typedef struct ry_op_desc {
 /* ---- plan lifetime ------------------------------------------------------------------------------------------- */
 
 int ry_abi_version(void);
+int ry_abi_sizeof(int which);                   /* 0: sizeof(ry_tensor_desc), 1: sizeof(ry_op_desc) -- binding self-check */
 const char *ry_last_error(void);            /* thread-local, valid until the next failing call on this thread */
 
 /* Copies the op list, packs the weights (bf16, UMMA K-major order) into plan-owned device memory on `device`. */
@@ -123,6 +124,12 @@ int ry_run_ops(ry_plan *plan, int first, int last, const float *image, float *pr
                float *raw2, void *stream);
 /* Number of kernel launches ry_forward issues for the bound shape (for bench.py's gpu_launches). */
 int ry_plan_launch_count(ry_plan *plan, int *n);
+
+/* Optional per-op timing for roofline reports: when on, ry_forward / ry_run_ops bracket every op with CUDA events on the
+ * caller's stream; ry_plan_op_times returns the last elapsed milliseconds per op (host array of n = number of ops) after
+ * the caller has synchronised the stream. */
+int ry_plan_set_profiling(ry_plan *plan, int on);
+int ry_plan_op_times(ry_plan *plan, float *ms_host, int n);
 
 /* non_max_suppression.  pred: fp32 [B,N,5+nc] (not modified).  out: fp32 [B,max_det,6] rows (x1,y1,x2,y2,conf,cls)
  * in score order, counts: int32 [B].  classes: HOST array or NULL.  iou_thres is compared in double like torchvision. */

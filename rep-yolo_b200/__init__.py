@@ -9,3 +9,4 @@ from .model import Model, IDetect, NativeEngine          # noqa: F401
 from .nms import non_max_suppression, nms_padded          # noqa: F401
 from ._lib import NativeError, lib                        # noqa: F401
 from .arch import rep_yolo_cfg                            # noqa: F401
+from .parallel import gather_detections, shard_bounds, to_list  # noqa: F401

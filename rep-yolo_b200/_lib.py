@@ -32,9 +32,9 @@ class OpDesc(C.Structure):
                 ('fparam', C.c_float * 8)]
 
 
-EXPORTS = ['ry_abi_version', 'ry_last_error', 'ry_plan_create', 'ry_plan_destroy', 'ry_plan_workspace_bytes',
+EXPORTS = ['ry_abi_version', 'ry_abi_sizeof', 'ry_last_error', 'ry_plan_create', 'ry_plan_destroy', 'ry_plan_workspace_bytes',
            'ry_plan_bind', 'ry_plan_tensor_info', 'ry_plan_num_candidates', 'ry_plan_launch_count', 'ry_forward',
-           'ry_run_ops', 'ry_nms_workspace_bytes', 'ry_nms']
+           'ry_run_ops', 'ry_plan_set_profiling', 'ry_plan_op_times', 'ry_nms_workspace_bytes', 'ry_nms']
 
 _lib = None
 
@@ -65,13 +65,19 @@ def lib():
     L.ry_plan_launch_count.argtypes = [vp, C.POINTER(i32)]
     L.ry_forward.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     L.ry_run_ops.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp, vp]
+    L.ry_plan_set_profiling.argtypes = [vp, i32]
+    L.ry_plan_op_times.argtypes = [vp, C.POINTER(C.c_float), i32]
     L.ry_nms_workspace_bytes.argtypes = [i32, i32, i32, i32, C.POINTER(sz)]
     L.ry_nms.argtypes = [vp, i32, i32, i32, C.c_float, C.c_double, vp, i32, i32, i32, i32, i32, vp, vp, vp, sz, vp]
     for name in EXPORTS:
-        if name not in ('ry_last_error', 'ry_plan_destroy', 'ry_abi_version'):
+        if name not in ('ry_last_error', 'ry_plan_destroy', 'ry_abi_version', 'ry_abi_sizeof'):
             getattr(L, name).restype = i32
     if L.ry_abi_version() != 1:
         raise NativeError('ABI version mismatch between _lib.py and librepyolo_b200.so')
+    L.ry_abi_sizeof.argtypes = [i32]
+    L.ry_abi_sizeof.restype = i32
+    if L.ry_abi_sizeof(0) != C.sizeof(TensorDesc) or L.ry_abi_sizeof(1) != C.sizeof(OpDesc):
+        raise NativeError('struct layout mismatch between _lib.py and include/repyolo_b200.h')
     _lib = L
     return L
 

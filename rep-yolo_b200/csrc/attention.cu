@@ -151,13 +151,13 @@ __global__ void __launch_bounds__(kAttnThreads) attn_line_kernel(const AttnParam
                 const size_t px = pix_of(i);
                 const int c = cg * 4;
                 if (MODE == MODE_ROW) {
-                    float *sc = p.scratch + px * (C + 2);
+                    float *sc = p.scratch + px * (C + 4);
                     *reinterpret_cast<float4 *>(sc + c) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
                     if (cg == 0) { sc[C] = mrow[i]; sc[C + 1] = srow[i]; }
                 } else {
                     float o[4] = {acc[r][0], acc[r][1], acc[r][2], acc[r][3]};
                     if (MODE == MODE_COL) {
-                        const float *sc = p.scratch + px * (C + 2);
+                        const float *sc = p.scratch + px * (C + 4);
                         const float4 ow = *reinterpret_cast<const float4 *>(sc + c);
                         const float mw = sc[C], sw = sc[C + 1], mh = mrow[i], sh = srow[i];
                         const float m = fmaxf(mh, mw);
@@ -211,7 +211,7 @@ void attn_qk_launch(const __nv_bfloat16 *x, int x_cs, int x_off, int C, int Cq, 
     attn_qk_kernel<<<(int)g, 256, 0, st>>>(x, x_cs, x_off, Cq, npix, wq, bq, wk, bk, s, t, q, k);
 }
 
-size_t crisscross_scratch_floats(int B, int H, int W, int C) { return (size_t)B * H * W * (C + 2); }
+size_t crisscross_scratch_floats(int B, int H, int W, int C) { return (size_t)B * H * W * (C + 4); }
 
 int crisscross_launch(const AttnParams &p, cudaStream_t st) {
     if (launch_line<MODE_ROW>(p, st)) return 1;

@@ -31,7 +31,7 @@ struct AttnParams {
     float gamma;
     __nv_bfloat16 *out;       // output map view
     int out_cs, out_off;
-    float *scratch;           // criss-cross row pass partials: [B*H*W, C + 2] fp32
+    float *scratch;           // criss-cross row pass partials: [B*H*W, C + 4] fp32 (16-byte aligned rows)
 };
 void attn_qk_launch(const __nv_bfloat16 *x, int x_cs, int x_off, int C, int Cq, size_t npix, const float *wq,
                     const float *bq, const float *wk, const float *bk, const float *s, const float *t, float *q, float *k,

@@ -82,6 +82,9 @@ struct ry_plan {
     CUtensorMap *d_tmaps = nullptr;
     size_t tmaps_cap = 0;
     int n_cand = 0;
+    // optional per-op CUDA-event timing (bench.py roofline): events[2*i], events[2*i+1] bracket op i
+    bool profiling = false;
+    std::vector<cudaEvent_t> events;
 };
 
 namespace ry {
@@ -396,6 +399,7 @@ using namespace ry;
 extern "C" {
 
 int ry_abi_version(void) { return RY_ABI_VERSION; }
+int ry_abi_sizeof(int which) { return which == 0 ? (int)sizeof(ry_tensor_desc) : (which == 1 ? (int)sizeof(ry_op_desc) : -1); }
 const char *ry_last_error(void) { return g_error.c_str(); }
 
 int ry_plan_create(const ry_tensor_desc *tensors, int n_tensors, const ry_op_desc *ops, int n_ops, const void *weights_host,
@@ -487,6 +491,7 @@ void ry_plan_destroy(ry_plan *p) {
     if (!p) return;
     if (p->d_weights) cudaFree(p->d_weights);
     if (p->d_tmaps) cudaFree(p->d_tmaps);
+    for (auto &e : p->events) cudaEventDestroy(e);
     delete p;
 }
 
@@ -577,9 +582,32 @@ int ry_run_ops(ry_plan *p, int first, int last, const float *image, float *pred,
     if (first < 0 || last > (int)p->ops.size() || first > last) RY_FAIL("run_ops: bad op range");
     float *raws[3] = {raw0, raw1, raw2};
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    for (int i = first; i < last; ++i)
+    for (int i = first; i < last; ++i) {
+        if (p->profiling) cudaEventRecord(p->events[2 * i], st);
         if (run_op(p, p->ops[i], image, pred, raws, st)) return 1;
+        if (p->profiling) cudaEventRecord(p->events[2 * i + 1], st);
+    }
     RY_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int ry_plan_set_profiling(ry_plan *p, int on) {
+    if (!p) RY_FAIL("set_profiling: NULL plan");
+    if (on && p->events.empty()) {
+        p->events.resize(2 * p->ops.size());
+        for (auto &e : p->events) RY_CUDA(cudaEventCreate(&e));
+    }
+    p->profiling = on != 0;
+    return 0;
+}
+
+int ry_plan_op_times(ry_plan *p, float *ms_host, int n) {
+    if (!p || !ms_host || n != (int)p->ops.size() || p->events.empty()) RY_FAIL("op_times: profiling was never enabled");
+    for (int i = 0; i < n; ++i) {
+        ms_host[i] = 0.0f;
+        if (cudaEventQuery(p->events[2 * i + 1]) == cudaSuccess) cudaEventElapsedTime(&ms_host[i], p->events[2 * i], p->events[2 * i + 1]);
+    }
+    cudaGetLastError();
     return 0;
 }
 

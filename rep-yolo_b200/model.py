@@ -95,6 +95,16 @@ class NativeEngine:
         N.check(N.lib().ry_plan_launch_count(self.handle, C.byref(n)), 'ry_plan_launch_count')
         return n.value
 
+    def set_profiling(self, on: bool):
+        N.check(N.lib().ry_plan_set_profiling(self.handle, int(on)), 'ry_plan_set_profiling')
+
+    def op_times_ms(self):
+        """per-op elapsed milliseconds of the last profiled run (call after synchronising the stream)"""
+        n = len(self.plan_ir.ops)
+        buf = (C.c_float * n)()
+        N.check(N.lib().ry_plan_op_times(self.handle, buf, n), 'ry_plan_op_times')
+        return list(buf)
+
     def tensor(self, t):
         """torch view of plan tensor ``t`` inside the bound workspace: [B, h, w, C] (maps) or [B, C] (vectors)."""
         off, h, w, c, dt = C.c_size_t(), C.c_int(), C.c_int(), C.c_int(), C.c_int()

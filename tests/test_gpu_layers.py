@@ -61,26 +61,37 @@ def test_groups_teacher_forced(bound):
 
 
 def test_detect_decode_teacher_forced(bound):
+    """Head 1x1 conv + decode fused in the GEMM epilogue.  Inputs: the oracle's fp32 feature maps normalised to rms 1
+    (random-weight Rep-YOLO can drive logits to +-1e3 where any bf16 operand rounding saturates the sigmoid).
+    (a) vs the oracle run on the same bf16-rounded operands: only fp32 accumulation order differs -> tight;
+    (b) vs the pure fp32 oracle: the stated decode tolerance of SURVEY.md 8d(4)."""
+    import torch.nn.functional as F
     from gpu_util import nchw_to_arena
     eng, outs, layers, fz, B, size = (bound[k] for k in ('eng', 'outs', 'layers', 'fz', 'B', 'size'))
     g = eng.plan_ir.groups[-1]
-    feats = [outs[62], outs[63], outs[64]]
+    feats = [o / o.pow(2).mean().sqrt() for o in (outs[62], outs[63], outs[64])]
     for (src, view), f in zip(g.inputs, feats):
         nchw_to_arena(eng, view, f)
     pred, raws = eng._outputs(B, size, size)
     eng.run_ops(g.first_op, g.last_op, pred=pred, raws=raws)
     torch.cuda.synchronize()
-    heads = O.run_fused_layer(fz, layers[-1], feats)
-    pred_ref, raws_ref = O.decode_heads(heads, fz['model.65.anchor_grid'])
     p = pred.cpu()
+    ag = fz['model.65.anchor_grid']
+    # (a) same operands
+    heads_b = [F.conv2d(f.bfloat16().float(), fz[f'model.65.m.{j}.weight'].bfloat16().float(), fz[f'model.65.m.{j}.bias'])
+               for j, f in enumerate(feats)]
+    pred_b, raws_b = O.decode_heads(heads_b, ag)
+    for a, b in zip(raws, raws_b):
+        assert a.shape == b.shape
+        assert bool(((a.cpu() - b).abs() <= 2e-4 * (1 + b.abs())).all()), float((a.cpu() - b).abs().max())
+    assert bool(((p - pred_b).abs() <= 2e-3 + 1e-4 * pred_b.abs()).all()), float((p - pred_b).abs().max())
+    # (b) fp32 oracle, stated tolerance
+    pred_ref, _ = O.decode_heads(O.run_fused_layer(fz, layers[-1], feats), ag)
     assert p.shape == pred_ref.shape
     assert float((p[..., :2] - pred_ref[..., :2]).abs().max()) <= 0.25
     dwh = (p[..., 2:4] - pred_ref[..., 2:4]).abs()
     assert bool((dwh <= 1e-2 * pred_ref[..., 2:4] + 0.05).all()), float(dwh.max())
     assert float((p[..., 4:] - pred_ref[..., 4:]).abs().max()) <= 4e-3
-    for a, b in zip(raws, raws_ref):
-        assert a.shape == b.shape
-        assert float((a.cpu() - b).abs().max()) <= 3e-2 * (1 + float(b.abs().max()))
 
 
 def test_idetect_fuseforward_signature(bound):
