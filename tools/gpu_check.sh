@@ -1,0 +1,23 @@
+#!/bin/bash
+# Run on the GPU box (via gpurun): GPU parity tests, a short bench, the ncu launch list of the same bench command and
+# one `ncu --set full` capture of the dominant kernel.  Outputs land in gpurun_out/.
+#   tools/gpu_check.sh [tag] [kernel-regex] [skip-launches]
+set -u
+TAG=${1:-r01}
+KRE=${2:-conv_umma_kernel}
+SKIP=${3:-0}
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -x -q > gpurun_out/gputests_$TAG.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/gputests_$TAG.log
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke_$TAG.log 2>&1; echo "smoke rc=$?"
+python bench.py --steps 10 --warmup 3 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; echo "bench rc=$?"
+cat gpurun_out/bench_$TAG.json
+python tools/profile_ops.py --out gpurun_out/ops_$TAG.txt > /dev/null 2> gpurun_out/prof_$TAG.err; echo "profile_ops rc=$?"
+BENCH="python bench.py --steps 3 --warmup 3 --no-cpu-baseline"
+$BENCH > gpurun_out/plain_$TAG.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -s 612 -c 420 --csv --log-file gpurun_out/launches_$TAG.csv $BENCH > gpurun_out/ncu_launches_$TAG.log 2>&1
+echo "ncu launches rc=$?"
+PROF="python tools/profile_ops.py --batch 64 --reps 1"
+$PROF > gpurun_out/plain2_$TAG.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:$KRE -s $SKIP -c 3 -f -o gpurun_out/prof_$TAG $PROF > gpurun_out/ncu_full_$TAG.log 2>&1
+echo "ncu full rc=$?"
+tail -3 gpurun_out/gputests_$TAG.log
