@@ -1,5 +1,7 @@
-// tcgen05 / TMEM / TMA implicit-GEMM convolution kernel (see conv_umma.cuh).
+// tcgen05 / TMEM / TMA implicit-GEMM convolution kernel (see conv_umma.cuh for the design).
 #include "conv_umma.cuh"
+
+#include <algorithm>
 
 #include "common.cuh"
 #include "ptx.cuh"
@@ -8,7 +10,8 @@ namespace ry {
 
 namespace {
 
-constexpr int kStageA = 128 * 128;   // 128 rows x 128 B (64 bf16 of K) per stage, whatever the swizzle span
+constexpr int kSmemLimit = 227 * 1024;
+constexpr int kBarrierBytes = 512;
 
 struct TileCoord {
     int w0, h0, n0, nc0;
@@ -24,49 +27,45 @@ __device__ __forceinline__ TileCoord tile_coord(const ConvArgs &p, int t) {
     return {wi * p.tw, hi * p.th, ni * p.tn, nt * p.BN};
 }
 
-__device__ __forceinline__ void store_epilogue(const ConvArgs &p, const float *v, int ng, size_t pix, int img) {
-    // v[16]: fp32 accumulators of output channels ng..ng+15 of one pixel
-    float x[16];
-    const float4 *b4 = reinterpret_cast<const float4 *>(p.bias + ng);
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// 8 accumulator columns -> bias, activation, optional residual / per-image vector -> 8 bf16 (one 16-byte chunk).
+//   t = acc*scale + sbias (sbias is pre-multiplied by scale: 0.5 for SiLU, 1 for identity)
+//   SiLU(x) = x*sigmoid(x) = h + h*tanh(h), h = x/2   (one MUFU.TANH instead of EX2 + RCP)
+__device__ __forceinline__ uint4 epi_chunk8(const ConvArgs &p, const uint32_t *raw, const float *sb, float scale, bool valid,
+                                           size_t pix, int img, int ch) {
+    float x[8];
+    const float4 b0 = *reinterpret_cast<const float4 *>(sb), b1 = *reinterpret_cast<const float4 *>(sb + 4);
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const float4 b = __ldg(b4 + q);
-        x[4 * q + 0] = v[4 * q + 0] + b.x;
-        x[4 * q + 1] = v[4 * q + 1] + b.y;
-        x[4 * q + 2] = v[4 * q + 2] + b.z;
-        x[4 * q + 3] = v[4 * q + 3] + b.w;
-    }
+    for (int i = 0; i < 8; ++i) x[i] = fmaf(__uint_as_float(raw[i]), scale, bb[i]);
     if (p.act == 1) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) x[i] = silu_f(x[i]);
+        for (int i = 0; i < 8; ++i) x[i] = fmaf(x[i], ptx::tanh_approx(x[i]), x[i]);
     }
-    const bool second = ng + 8 < p.cout;
-    if (p.res != nullptr) {
-        const uint4 *r = reinterpret_cast<const uint4 *>(p.res + pix * p.res_cs + p.res_off + ng);
-        uint4 r0 = __ldg(r), r1 = second ? __ldg(r + 1) : make_uint4(0, 0, 0, 0);
-        const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+    if (p.res != nullptr && valid) {
+        const uint4 r = __ldg(reinterpret_cast<const uint4 *>(p.res + pix * p.res_cs + p.res_off + ch));
+        const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < 4; ++i) {
             const float2 f = unpack_bf16x2(rw[i]);
             x[2 * i] += f.x;
             x[2 * i + 1] += f.y;
         }
     }
-    if (p.bvec != nullptr) {
-        const float *bv = p.bvec + (size_t)img * p.bvec_cs + p.bvec_off + ng;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) x[i] += (ng + i < p.cout) ? __ldg(bv + i) : 0.0f;
+    if (p.bvec != nullptr && valid) {
+        const float4 *bv = reinterpret_cast<const float4 *>(p.bvec + (size_t)img * p.bvec_cs + p.bvec_off + ch);
+        const float4 v0 = __ldg(bv), v1 = __ldg(bv + 1);
+        x[0] += v0.x; x[1] += v0.y; x[2] += v0.z; x[3] += v0.w;
+        x[4] += v1.x; x[5] += v1.y; x[6] += v1.z; x[7] += v1.w;
     }
-    const int ch = ng < p.split_at ? p.off0 + ng : p.off1 + (ng - p.split_at);
-    uint4 *dst = reinterpret_cast<uint4 *>(p.out + pix * p.out_cs + ch);
-    dst[0] = make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]), pack_bf16x2(x[6], x[7]));
-    if (second)
-        dst[1] = make_uint4(pack_bf16x2(x[8], x[9]), pack_bf16x2(x[10], x[11]), pack_bf16x2(x[12], x[13]),
-                            pack_bf16x2(x[14], x[15]));
+    return make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]), pack_bf16x2(x[6], x[7]));
 }
 
 // IDetect.fuseforward decode (reference models/yolo.py:139-156): same op order, fp32.
-__device__ __forceinline__ void detect_epilogue(const ConvArgs &p, const float *v, int j0, size_t pix) {
+__device__ __forceinline__ void detect_epilogue(const ConvArgs &p, const uint32_t *raw, int j0, size_t pix) {
     const int b = (int)(pix / p.img_hw);
     const int rem = (int)(pix - (size_t)b * p.img_hw);
     const int gy = rem / p.img_w, gx = rem - gy * p.img_w;
@@ -75,7 +74,7 @@ __device__ __forceinline__ void detect_epilogue(const ConvArgs &p, const float *
         const int j = j0 + i;
         if (j >= p.na * p.no) break;
         const int a = j / p.no, o = j - a * p.no;
-        const float t = v[i] + __ldg(p.bias + j);
+        const float t = __uint_as_float(raw[i]) + __ldg(p.bias + j);
         if (p.raw != nullptr) p.raw[(((size_t)b * p.na + a) * p.img_hw + rem) * p.no + o] = t;
         const float s = 1.0f / (1.0f + expf(-t));
         float y;
@@ -91,38 +90,47 @@ __device__ __forceinline__ void detect_epilogue(const ConvArgs &p, const float *
 __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const __grid_constant__ ConvArgs p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int stage_bytes = kStageA + p.BN * 128;
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)p.stages * stage_bytes);
-    uint64_t *empty = full + p.stages;
-    uint64_t *tfull = empty + p.stages;
-    uint64_t *tempty = tfull + 2;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
+    const int nb_slots = p.b_resident ? p.kblocks : p.b_stages;
+    uint8_t *sA = smem;
+    uint8_t *sB = sA + (size_t)p.a_stages * p.a_stage_bytes;
+    uint8_t *sStage = sB + (size_t)nb_slots * p.b_stage_bytes;
+    float *sbias = reinterpret_cast<float *>(sStage + 4 * (size_t)p.stage_buf_bytes);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(sbias) + ((p.cout_pad * 4 + 127) & ~127));
+    uint64_t *fullA = bars, *emptyA = fullA + 8, *fullB = emptyA + 8, *emptyB = fullB + 8;
+    uint64_t *tfull = emptyB + 8, *tempty = tfull + 2, *bres = tempty + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bres + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int G = 64 / p.kb;                       // K blocks per pipeline stage
-    const int row_bytes = p.kb * 2;
-    const int a_sub = 128 * row_bytes, b_sub = p.BN * row_bytes;
-    const int n_iters = (p.kblocks + G - 1) / G;
+    const int rb = p.kb * 2;                                   // bytes per operand row == swizzle span
     const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_ntiles;
+    const int ksteps_full = p.kb / 16;
     uint32_t tmem_cols = 32;
     while (tmem_cols < 2u * p.BN) tmem_cols <<= 1;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < p.stages; ++s) {
-            ptx::mbar_init(full + s, 1);
-            ptx::mbar_init(empty + s, 1);
+        for (int s = 0; s < 8; ++s) {
+            ptx::mbar_init(fullA + s, 1);
+            ptx::mbar_init(emptyA + s, 1);
+            ptx::mbar_init(fullB + s, 1);
+            ptx::mbar_init(emptyB + s, 1);
         }
         for (int a = 0; a < 2; ++a) {
             ptx::mbar_init(tfull + a, 1);
-            ptx::mbar_init(tempty + a, 4);
+            ptx::mbar_init(tempty + a, 8);
         }
+        ptx::mbar_init(bres, 1);
         ptx::fence_mbar_init();
-        for (int i = 0; i < p.ntaps && i < 4; ++i) ptx::prefetch_tmap(p.amap + i);
+        ptx::prefetch_tmap(p.amap);
         ptx::prefetch_tmap(p.wmap);
+        if (p.mode == 0) ptx::prefetch_tmap(p.omap);
     }
     if (warp == 1) {
         ptx::tmem_alloc(tmem_slot, tmem_cols);
         ptx::tmem_relinquish();
+    }
+    {
+        const float scale = p.act == 1 ? 0.5f : 1.0f;
+        for (int i = threadIdx.x; i < p.cout_pad; i += blockDim.x) sbias[i] = __ldg(p.bias + i) * scale;
     }
     ptx::tc_fence_before();
     __syncthreads();
@@ -130,69 +138,166 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const __grid
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
-            const uint32_t box_rows = p.tw * p.th * p.tn;
-            int s = 0;
-            uint32_t ph = 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-                const TileCoord tc = tile_coord(p, t);
-                for (int it = 0; it < n_iters; ++it) {
-                    const int kb0 = it * G;
-                    const int nsub = min(G, p.kblocks - kb0);
-                    ptx::mbar_wait(empty + s, ph ^ 1);
-                    ptx::mbar_expect_tx(full + s, nsub * (box_rows + p.BN) * row_bytes);
-                    uint8_t *sa = smem + (size_t)s * stage_bytes, *sb = sa + kStageA;
-                    for (int j = 0; j < nsub; ++j) {
-                        const int kbi = kb0 + j;
-                        const int tap = kbi / p.cblk, cb = kbi - tap * p.cblk;
-                        ptx::tma_load_4d(sa + j * a_sub, p.amap + p.tap_map[tap], full + s, cb * p.kb,
-                                         tc.w0 + p.tap_dw[tap], tc.h0 + p.tap_dh[tap], tc.n0);
-                        ptx::tma_load_2d(sb + j * b_sub, p.wmap, full + s, kbi * p.kb, tc.nc0);
+        // ===================== TMA producer (whole warp in uniform control flow, one elected lane issues) ==========
+        const bool issuer = ptx::elect_one();
+        if (p.b_resident && issuer) {
+            ptx::mbar_expect_tx(bres, (uint32_t)(p.kblocks * p.b_stage_bytes));
+            for (int kbi = 0; kbi < p.kblocks; ++kbi)
+                ptx::tma_load_2d(sB + (size_t)kbi * p.b_stage_bytes, p.wmap, bres, kbi * p.kb, 0);
+        }
+        int sa = 0, sb = 0;
+        uint32_t pha = 0, phb = 0;
+        const bool stream_b = !p.b_resident;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            const TileCoord tc = tile_coord(p, t);
+            if (p.a_mode == A_HALO) {
+                for (int c = 0; c < p.cblk; ++c) {
+                    ptx::mbar_wait(emptyA + sa, pha ^ 1);
+                    if (issuer) {
+                        ptx::mbar_expect_tx(fullA + sa, (uint32_t)p.a_box_bytes);
+                        ptx::tma_load_4d(sA + (size_t)sa * p.a_stage_bytes, p.amap, fullA + sa, c * p.kb, tc.w0 - 1, tc.h0 - 1, tc.n0);
                     }
-                    if (++s == p.stages) { s = 0; ph ^= 1; }
+                    if (++sa == p.a_stages) { sa = 0; pha ^= 1; }
+                    if (stream_b) {
+                        for (int tap = 0; tap < 9; ++tap) {
+                            ptx::mbar_wait(emptyB + sb, phb ^ 1);
+                            if (issuer) {
+                                ptx::mbar_expect_tx(fullB + sb, (uint32_t)p.b_stage_bytes);
+                                ptx::tma_load_2d(sB + (size_t)sb * p.b_stage_bytes, p.wmap, fullB + sb, (tap * p.cblk + c) * p.kb, tc.nc0);
+                            }
+                            if (++sb == p.b_stages) { sb = 0; phb ^= 1; }
+                        }
+                    }
+                }
+            } else {
+                int tap = 0, cb = 0;
+                for (int kbi = 0; kbi < p.kblocks; ++kbi) {
+                    ptx::mbar_wait(emptyA + sa, pha ^ 1);
+                    if (issuer) {
+                        ptx::mbar_expect_tx(fullA + sa, (uint32_t)p.a_box_bytes);
+                        ptx::tma_load_4d(sA + (size_t)sa * p.a_stage_bytes, p.amap + p.tap_map[tap], fullA + sa, cb * p.kb,
+                                         tc.w0 + p.tap_dw[tap], tc.h0 + p.tap_dh[tap], tc.n0);
+                    }
+                    if (++sa == p.a_stages) { sa = 0; pha ^= 1; }
+                    if (stream_b) {
+                        ptx::mbar_wait(emptyB + sb, phb ^ 1);
+                        if (issuer) {
+                            ptx::mbar_expect_tx(fullB + sb, (uint32_t)p.b_stage_bytes);
+                            ptx::tma_load_2d(sB + (size_t)sb * p.b_stage_bytes, p.wmap, fullB + sb, kbi * p.kb, tc.nc0);
+                        }
+                        if (++sb == p.b_stages) { sb = 0; phb ^= 1; }
+                    }
+                    if (++cb == p.cblk) { cb = 0; ++tap; }
                 }
             }
         }
         __syncwarp();
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            const uint32_t idesc = ptx::umma_idesc_bf16(128, p.BN);
-            int s = 0, acc = 0;
-            uint32_t ph = 0, aph = 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-                ptx::mbar_wait(tempty + acc, aph ^ 1);
+        // ===================== MMA issuer (whole warp in uniform control flow, one elected lane issues) =============
+        // Descriptors are built once; per stage / tap / K step only their low word (start address >> 4) moves.
+        const bool issuer = ptx::elect_one();
+        const uint32_t idesc = ptx::umma_idesc_bf16(128, p.BN);
+        const uint32_t a_sbo = (p.a_mode == A_HALO ? p.halo_w : 8) * rb;
+        const uint64_t a_desc0 = ptx::umma_smem_desc(ptx::smem_u32(sA), rb, a_sbo);
+        const uint64_t b_desc0 = ptx::umma_smem_desc(ptx::smem_u32(sB), rb, 8 * rb);
+        const uint32_t a_hi = (uint32_t)(a_desc0 >> 32), b_hi = (uint32_t)(b_desc0 >> 32);
+        const uint32_t a_lo0 = (uint32_t)a_desc0, b_lo0 = (uint32_t)b_desc0;
+        const uint32_t a_inc = (uint32_t)p.a_stage_bytes >> 4, b_inc = (uint32_t)p.b_stage_bytes >> 4;
+        const uint32_t pix_inc = (uint32_t)rb >> 4;                     // one halo pixel
+        const uint32_t row_inc = (uint32_t)(p.halo_w * rb) >> 4;        // one halo row
+        const bool stream_b = !p.b_resident;
+        const bool halo = p.a_mode == A_HALO;
+        const int n_a = halo ? p.cblk : p.kblocks;
+        const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+        if (p.b_resident) {
+            ptx::mbar_wait(bres, 0);
+            ptx::tc_fence_after();
+        }
+        int sa = 0, sb = 0, acc = 0;
+        uint32_t pha = 0, phb = 0, aph = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            ptx::mbar_wait(tempty + acc, aph ^ 1);
+            ptx::tc_fence_after();
+            const uint32_t d_tmem = tmem_u + acc * p.BN;
+            uint32_t accumulate = 0;
+            int c = 0;
+            for (int ia = 0; ia < n_a; ++ia) {
+                const int ks = (c == p.cblk - 1) ? p.ksteps_last : ksteps_full;
+                ptx::mbar_wait(fullA + sa, pha);
                 ptx::tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * p.BN;
-                uint32_t accumulate = 0;
-                for (int it = 0; it < n_iters; ++it) {
-                    const int nsub = min(G, p.kblocks - it * G);
-                    ptx::mbar_wait(full + s, ph);
-                    ptx::tc_fence_after();
-                    const uint32_t sa = ptx::smem_u32(smem + (size_t)s * stage_bytes), sb = sa + kStageA;
-                    for (int j = 0; j < nsub; ++j) {
-                        for (int k = 0; k < p.kb / 16; ++k) {
-                            const uint64_t da = ptx::umma_smem_desc(sa + j * a_sub + k * 32, row_bytes);
-                            const uint64_t db = ptx::umma_smem_desc(sb + j * b_sub + k * 32, row_bytes);
-                            ptx::umma_bf16(d_tmem, da, db, idesc, accumulate);
-                            accumulate = 1;
+                const uint32_t a_lo = a_lo0 + sa * a_inc;
+                if (halo) {
+                    uint32_t a_row = a_lo, b_idx = c;
+#pragma unroll 1
+                    for (int th = 0; th < 3; ++th) {
+#pragma unroll
+                        for (int tw = 0; tw < 3; ++tw) {
+                            uint32_t b_lo;
+                            if (stream_b) {
+                                ptx::mbar_wait(fullB + sb, phb);
+                                ptx::tc_fence_after();
+                                b_lo = b_lo0 + sb * b_inc;
+                            } else {
+                                b_lo = b_lo0 + b_idx * b_inc;
+                            }
+                            if (issuer) {
+                                const uint32_t a_t = a_row + tw * pix_inc;
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    if (k < ks) {
+                                        ptx::umma_bf16_lohi(d_tmem, a_t + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc, accumulate);
+                                        accumulate = 1;
+                                    }
+                                }
+                                if (stream_b) ptx::umma_commit(emptyB + sb);
+                            }
+                            if (stream_b && ++sb == p.b_stages) { sb = 0; phb ^= 1; }
+                            b_idx += p.cblk;
                         }
+                        a_row += row_inc;
                     }
-                    ptx::umma_commit(empty + s);      // frees the smem stage once these MMAs retire
-                    if (++s == p.stages) { s = 0; ph ^= 1; }
+                    accumulate = 1;
+                } else {
+                    uint32_t b_lo;
+                    if (stream_b) {
+                        ptx::mbar_wait(fullB + sb, phb);
+                        ptx::tc_fence_after();
+                        b_lo = b_lo0 + sb * b_inc;
+                    } else {
+                        b_lo = b_lo0 + ia * b_inc;
+                    }
+                    if (issuer) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            if (k < ks) {
+                                ptx::umma_bf16_lohi(d_tmem, a_lo + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc, accumulate);
+                                accumulate = 1;
+                            }
+                        }
+                        if (stream_b) ptx::umma_commit(emptyB + sb);
+                    }
+                    accumulate = 1;
+                    if (stream_b && ++sb == p.b_stages) { sb = 0; phb ^= 1; }
                 }
-                ptx::umma_commit(tfull + acc);        // accumulator ready for the epilogue
-                if (++acc == 2) { acc = 0; aph ^= 1; }
+                if (issuer) ptx::umma_commit(emptyA + sa);    // frees the A stage once these MMAs retire
+                if (++sa == p.a_stages) { sa = 0; pha ^= 1; }
+                if (++c == p.cblk) c = 0;
             }
+            if (issuer) ptx::umma_commit(tfull + acc);        // accumulator ready for the epilogue
+            if (++acc == 2) { acc = 0; aph ^= 1; }
         }
         __syncwarp();
     } else {
-        // ===================== epilogue (4 warps, TMEM lane quarter = warp % 4) =====================
+        // ===================== epilogue: 2 column groups x 4 warps (TMEM lane quarter = warp % 4) =====================
+        const int e = warp - 2;
+        const int grp = e >> 2;
         const int quarter = warp & 3;
+        const bool leader = (e & 3) == 0 && lane == 0;
         const int row = quarter * 32 + lane;
         const int w_in = row % p.tw, h_in = (row / p.tw) % p.th, n_in = row / (p.tw * p.th);
-        int acc = 0;
+        const float scale = p.act == 1 ? 0.5f : 1.0f;
+        const uint32_t stage_u = ptx::smem_u32(sStage) + grp * 2 * p.stage_buf_bytes;
+        int acc = 0, bufsel = 0;
         uint32_t aph = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
             const TileCoord tc = tile_coord(p, t);
@@ -203,20 +308,57 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const __grid
             ptx::mbar_wait(tfull + acc, aph);
             ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + acc * p.BN + ((uint32_t)(quarter * 32) << 16);
-            for (int c = 0; c < p.BN / 16; ++c) {
-                float v[16];
-                ptx::tmem_ld16(taddr + c * 16, v);
-                const int ng = tc.nc0 + c * 16;
-                if (valid && ng < p.cout) {
-                    if (p.mode == 0) store_epilogue(p, v, ng, pix, img);
-                    else detect_epilogue(p, v, ng, pix);
+            if (p.mode == 0) {
+                for (int si = 0; si < p.nseg[grp]; ++si) {
+                    const ConvSeg sg = p.seg[grp][si];
+                    const uint32_t buf = stage_u + bufsel * p.stage_buf_bytes;
+                    if (leader) ptx::bulk_wait_read<1>();           // the store that last read this buffer is done
+                    ptx::bar_sync(1 + grp, 128);
+                    const uint32_t rowoff = (uint32_t)row * (uint32_t)(sg.ncol * 2);
+                    for (int c0 = 0; c0 < sg.ncol; c0 += 16) {
+                        uint32_t raw[16];
+                        const int col = sg.col0 + c0;
+                        if (sg.ncol - c0 >= 16) {
+                            ptx::tmem_ld16_nowait(taddr + col, raw);
+                            ptx::tmem_ld_wait();
+#pragma unroll
+                            for (int j = 0; j < 2; ++j) {
+                                const uint4 o = epi_chunk8(p, raw + 8 * j, sbias + tc.nc0 + col + 8 * j, scale, valid, pix, img,
+                                                           tc.nc0 + col + 8 * j);
+                                uint32_t lin = rowoff + (uint32_t)(c0 * 2 + j * 16);
+                                lin ^= ((lin >> 7) & (uint32_t)sg.swz) << 4;
+                                st_shared_v4(buf + lin, o);
+                            }
+                        } else {
+                            ptx::tmem_ld8_nowait(taddr + col, raw);
+                            ptx::tmem_ld_wait();
+                            const uint4 o = epi_chunk8(p, raw, sbias + tc.nc0 + col, scale, valid, pix, img, tc.nc0 + col);
+                            uint32_t lin = rowoff + (uint32_t)(c0 * 2);
+                            lin ^= ((lin >> 7) & (uint32_t)sg.swz) << 4;
+                            st_shared_v4(buf + lin, o);
+                        }
+                    }
+                    ptx::fence_proxy_async();
+                    ptx::bar_sync(1 + grp, 128);
+                    if (leader) {
+                        ptx::tma_store_4d(p.omap + sg.map, reinterpret_cast<const void *>(sStage + (size_t)(grp * 2 + bufsel) * p.stage_buf_bytes),
+                                          sg.chan + tc.nc0, tc.w0, tc.h0, tc.n0);
+                        ptx::bulk_commit();
+                    }
+                    bufsel ^= 1;
                 }
+            } else {
+                uint32_t raw[16];
+                ptx::tmem_ld16_nowait(taddr + grp * 16, raw);
+                ptx::tmem_ld_wait();
+                if (valid && grp * 16 < p.cout) detect_epilogue(p, raw, grp * 16, pix);
             }
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(tempty + acc);
             if (++acc == 2) { acc = 0; aph ^= 1; }
         }
+        if (leader) ptx::bulk_wait_read<0>();                       // staging must outlive the last TMA store's read
     }
 
     ptx::tc_fence_before();
@@ -229,23 +371,48 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const __grid
 
 }  // namespace
 
-int conv_pick_stages(int BN) {
-    const int stage_bytes = kStageA + BN * 128;
-    int s = (200 * 1024) / stage_bytes;
-    return s > 8 ? 8 : (s < 2 ? 2 : s);
+size_t conv_smem_bytes(const ConvArgs &a) {
+    const int nb = a.b_resident ? a.kblocks : a.b_stages;
+    return (size_t)a.a_stages * a.a_stage_bytes + (size_t)nb * a.b_stage_bytes + 4 * (size_t)a.stage_buf_bytes +
+           ((a.cout_pad * 4 + 127) & ~127) + kBarrierBytes + 1024;
 }
 
-size_t conv_smem_bytes(int BN, int stages) {
-    return (size_t)stages * (kStageA + BN * 128) + (2 * stages + 4) * sizeof(uint64_t) + 16 + 1024;
+int conv_plan_smem(ConvArgs &a, int max_seg_cols) {
+    const int rb = a.kb * 2;
+    const int box_rows = a.a_mode == A_HALO ? a.halo_w * (a.th + 2) : a.tw * a.th * a.tn;
+    a.a_box_bytes = box_rows * rb;
+    a.a_stage_bytes = a.a_mode == A_HALO ? ((a.a_box_bytes + 1023) & ~1023) : 128 * rb;
+    a.b_stage_bytes = a.BN * rb;
+    a.stage_buf_bytes = a.mode == 0 ? ((128 * max_seg_cols * 2 + 1023) & ~1023) : 0;
+    const long fixed = 4L * a.stage_buf_bytes + ((a.cout_pad * 4 + 127) & ~127) + kBarrierBytes + 1024;
+    const long avail = kSmemLimit - fixed;
+    const long b_total = (long)a.kblocks * a.b_stage_bytes;
+    const int a_per_tile = a.a_mode == A_HALO ? a.cblk : a.kblocks;
+    a.b_resident = (a.n_ntiles == 1 && b_total <= 100 * 1024 && avail - b_total >= 2L * a.a_stage_bytes) ? 1 : 0;
+    if (a.b_resident) {
+        a.b_stages = 0;
+        a.a_stages = (int)std::min<long>(8, (avail - b_total) / a.a_stage_bytes);
+        a.a_stages = std::min(a.a_stages, std::max(2, 6 * a_per_tile));
+    } else if (a.a_mode == A_HALO) {
+        a.a_stages = a.cblk >= 2 ? 3 : 2;
+        while (a.a_stages > 2 && avail - (long)a.a_stages * a.a_stage_bytes < 4L * a.b_stage_bytes) --a.a_stages;
+        a.b_stages = (int)std::min<long>(8, (avail - (long)a.a_stages * a.a_stage_bytes) / a.b_stage_bytes);
+        if (a.b_stages < 2) return 1;
+    } else {
+        const int n = (int)std::min<long>(8, avail / (a.a_stage_bytes + a.b_stage_bytes));
+        if (n < 2) return 1;
+        a.a_stages = a.b_stages = n;
+    }
+    return a.a_stages >= 2 ? 0 : 1;
 }
 
 void conv_launch(const ConvArgs &a, int grid, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
         attr_set = true;
     }
-    conv_umma_kernel<<<grid, kConvThreads, conv_smem_bytes(a.BN, a.stages), stream>>>(a);
+    conv_umma_kernel<<<grid, kConvThreads, conv_smem_bytes(a), stream>>>(a);
 }
 
 }  // namespace ry

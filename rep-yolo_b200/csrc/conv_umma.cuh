@@ -1,10 +1,24 @@
 // Implicit-GEMM convolution (1x1, 3x3 s1/s2) for NHWC bf16 activations on the 5th-gen tensor cores.
 //   D[pixel, cout] = sum_{tap, cin} A[pixel + tap, cin] * W[cout, tap, cin]
-// A tiles are fetched by TMA as shifted 4-D boxes of the activation tensor (zero fill outside the image = conv padding),
-// W tiles by 2-D TMA; both land in 32/64/128-byte-swizzled K-major shared memory and are consumed by tcgen05.mma with the
-// fp32 accumulator in TMEM (double buffered).  One persistent CTA per SM: warp 0 = TMA producer, warp 1 = MMA issuer,
-// warps 2..5 = epilogue (TMEM -> registers -> bias/SiLU/residual/broadcast-add -> bf16 NHWC at a channel offset, or the
-// Detect decode).
+// One persistent CTA per SM, 10 warps: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer, warps 2..9 = epilogue.
+//
+// A operand (activations), two fetch modes:
+//   A_BOX   one TMA box per (tap, K block): [tn][th][tw] pixels x kb channels, shifted by the tap, zero fill outside the
+//           image = conv padding.  Used by 1x1 convs (one "tap"), stride-2 3x3 (four parity-phase maps) and 3x3 on small
+//           maps.  Re-reads the input once per tap through L2.
+//   A_HALO  3x3 s1 on maps with W % 8 == 0: ONE TMA box per K block brings the (8+2) x (16+2) pixel halo of an
+//           8 wide x 16 high output tile; the nine taps are nine tcgen05.mma descriptor windows into that tile (start
+//           address shifted by (dh*10 + dw) pixels, 8-row groups 10 pixels apart).  The input crosses L2 1.4x, not 9x.
+// Channel counts that are not a multiple of the K block are padded by TMA out-of-bounds zero fill (the tensor map's
+// channel extent is the view length), so every cin > 32 runs 128-byte-swizzled 64-channel K blocks.
+//
+// B operand (weights, packed [cout_pad][tap][cblk*kb] bf16): resident in shared memory for the whole kernel when it fits
+// (small-channel layers: no per-tile weight re-fetch), otherwise streamed through its own ring.
+//
+// Epilogue: TMEM -> registers -> +bias, SiLU (0.5x(1+tanh(0.5x)), one MUFU), residual / per-image vector add -> bf16 ->
+// swizzled shared-memory staging -> TMA store into a channel range of the NHWC output (concat slots, GSConv shuffle
+// halves).  Two column groups of four warps work on disjoint accumulator columns.  The Detect head (mode 1) decodes in
+// registers and writes pred / raw rows directly.
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -12,31 +26,49 @@
 
 namespace ry {
 
-constexpr int kConvThreads = 192;
+constexpr int kConvThreads = 320;
 constexpr int kConvMaxTaps = 9;
+constexpr int kConvMaxSegs = 8;      // store segments per epilogue column group
+constexpr int kHaloTw = 8, kHaloTh = 16;
+
+enum { A_BOX = 0, A_HALO = 1 };
+
+struct ConvSeg {
+    int16_t col0, ncol;      // accumulator columns [col0, col0+ncol) of the N tile; ncol in {8, 16, 32, 64}
+    int32_t chan;            // absolute channel in the output tensor (n-tile offset added at run time)
+    int16_t map;             // index into omap[]
+    int16_t swz;             // XOR mask of the staging layout: 7 / 3 / 1 / 0 for 128 / 64 / 32 / 16-byte rows
+};
 
 struct ConvArgs {
-    const CUtensorMap *amap;   // up to 4 activation maps (stride-2 convs use the 4 parity phases of the input)
-    const CUtensorMap *wmap;   // packed weights [Cout_pad][K_pad]
+    const CUtensorMap *amap;   // activation maps (1, or the 4 parity phases of a stride-2 conv)
+    const CUtensorMap *wmap;   // packed weights [Cout_pad][K_pad], box {kb, BN}
+    const CUtensorMap *omap;   // output store maps (box widths 64/32/16/8 channels as needed)
+    int a_mode;                // A_BOX / A_HALO
     int kb;                    // channels per K block (16/32/64) == swizzle span / 2
     int cblk;                  // K blocks per tap
     int ntaps;
     int kblocks;               // ntaps * cblk
+    int ksteps_last;           // K=16 MMA steps holding real channels in the last K block of a tap
     int8_t tap_map[kConvMaxTaps], tap_dh[kConvMaxTaps], tap_dw[kConvMaxTaps];
-    int tw, th, tn;            // box (tile) extent in w, h, image
+    int tw, th, tn;            // output tile extent in w, h, image
     int tiles_w, tiles_h, tiles_n;
     int n_ntiles, BN;          // output-channel tiling
     int Wo, Ho, Bo;            // logical output extent the tile grid covers (1x1: Wo = B*H*W, Ho = Bo = 1)
     int img_w, img_hw;         // true W and H*W of the output map
-    int stages;
+    int halo_w;                // pixels per halo row (A_HALO)
+    int a_stage_bytes, a_stages, a_box_bytes;
+    int b_stage_bytes, b_stages, b_resident;
+    int stage_buf_bytes;       // epilogue staging: 2 groups x 2 buffers of this size
     int mode;                  // 0 = bf16 NHWC store, 1 = Detect decode
     const float *bias;         // [Cout_pad]
-    __nv_bfloat16 *out;
-    int out_cs, off0, off1, split_at, cout;
+    int cout, cout_pad;
     int act;
-    const __nv_bfloat16 *res;  // optional residual (same pixel grid)
+    int nseg[2];
+    ConvSeg seg[2][kConvMaxSegs];
+    const __nv_bfloat16 *res;  // optional residual (same pixel grid), added after the activation
     int res_cs, res_off;
-    const float *bvec;         // optional per-image vector [B][bvec_cs]
+    const float *bvec;         // optional per-image vector [B][bvec_cs], added after the activation
     int bvec_cs, bvec_off;
     float *pred, *raw;         // Detect outputs
     int no, na, row_off, rows_total;
@@ -44,8 +76,10 @@ struct ConvArgs {
     float anchors[6];
 };
 
-size_t conv_smem_bytes(int BN, int stages);
-int conv_pick_stages(int BN);
+size_t conv_smem_bytes(const ConvArgs &a);
+// Fills a_stage_bytes / a_stages / b_* / stage_buf_bytes from the geometry already in `a`; max_seg_cols = widest store
+// segment.  Returns non-zero when the shape does not fit.
+int conv_plan_smem(ConvArgs &a, int max_seg_cols);
 void conv_launch(const ConvArgs &a, int grid, cudaStream_t stream);
 
 }  // namespace ry

@@ -7,6 +7,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -51,7 +52,7 @@ struct Tensor {
 };
 
 struct ConvPacked {          // shape-independent part of a CONV / DETECT op
-    int kb = 0, cblk = 0, ntaps = 0, BN = 0, n_ntiles = 0, k_pad = 0, cout_pad = 0;
+    int kb = 0, cblk = 0, ksteps_last = 0, ntaps = 0, BN = 0, n_ntiles = 0, k_pad = 0, cout_pad = 0;
     size_t w_dev = 0, b_dev = 0;   // byte offsets in the device weight buffer
 };
 
@@ -62,7 +63,7 @@ struct Op {
     // shape-dependent (filled by bind)
     ConvArgs ca;
     int grid = 0;
-    int tmap_first = -1;
+    int tmap_first = -1, n_amaps = 1;
     int launches = 0;
 };
 
@@ -107,8 +108,11 @@ int pack_conv(const ry_op_desc &d, const unsigned char *host, size_t host_bytes,
     if (d.w_off < 0 || d.b_off < 0 || (size_t)d.w_off + (size_t)cout * cin * k * k * 4 > host_bytes ||
         (size_t)d.b_off + (size_t)cout * 4 > host_bytes)
         RY_FAIL("conv: weight offsets out of range");
-    cp.kb = (cin % 64 == 0) ? 64 : (cin % 32 == 0 ? 32 : 16);
+    // K block = swizzle span; a partial last block is completed by TMA out-of-bounds zero fill (activations) and by the
+    // zero padding of the packed weights
+    cp.kb = cin > 32 ? 64 : (cin > 16 ? 32 : 16);
     cp.cblk = (cin + cp.kb - 1) / cp.kb;
+    cp.ksteps_last = (cin - (cp.cblk - 1) * cp.kb + 15) / 16;
     cp.ntaps = k * k;
     cp.k_pad = cp.ntaps * cp.cblk * cp.kb;
     const int c16 = (cout + 15) / 16 * 16;
@@ -151,11 +155,12 @@ void pick_tile(int B, int Ho, int Wo, int *tw, int *th, int *tn) {
 }
 
 int encode_map(CUtensorMap *m, void *base, int rank, const cuuint64_t *dims, const cuuint64_t *strides_bytes,
-               const cuuint32_t *box, int kb) {
+               const cuuint32_t *box, int kb) {   // kb = inner box extent in bf16 elements: 64/32/16 -> 128/64/32-byte swizzle, 8 -> none
     EncodeTiledFn enc = get_encode();
     if (!enc) RY_FAIL("cuTensorMapEncodeTiled entry point not available (driver too old?)");
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    const CUtensorMapSwizzle sw = kb == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (kb == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+    const CUtensorMapSwizzle sw = kb == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                  : (kb == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : (kb == 16 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE));
     const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, base, dims, strides_bytes, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -176,6 +181,40 @@ inline __nv_bfloat16 *bf(ry_plan *p, int t) { return reinterpret_cast<__nv_bfloa
 inline float *f32(ry_plan *p, int t) { return reinterpret_cast<float *>(p->ws + p->tensors[t].offset); }
 inline const float *wf(ry_plan *p, size_t off) { return reinterpret_cast<const float *>(p->d_weights + off); }
 
+// Output channels of one N tile -> store segments (power-of-two widths, each with its own swizzled staging layout and TMA
+// store map), spread over the two epilogue column groups.
+struct OutPiece { int col0, len, chan; };
+
+void build_segments(ConvArgs &a, const OutPiece *pieces, int n_pieces, int max_cols, int widths[4], int *n_widths) {
+    int total = 0;
+    for (int i = 0; i < n_pieces; ++i) total += pieces[i].len;
+    int wmax = 8;
+    while (wmax * 2 <= max_cols && wmax * 2 <= std::max(8, total / 2)) wmax *= 2;
+    struct S { int col0, ncol, chan; };
+    std::vector<S> segs;
+    for (int i = 0; i < n_pieces; ++i)
+        for (int c = 0; c < pieces[i].len;) {
+            int w = wmax;
+            while (w > pieces[i].len - c) w /= 2;
+            segs.push_back({pieces[i].col0 + c, w, pieces[i].chan + c});
+            c += w;
+        }
+    std::stable_sort(segs.begin(), segs.end(), [](const S &x, const S &y) { return x.ncol > y.ncol; });
+    *n_widths = 0;
+    int load[2] = {0, 0};
+    a.nseg[0] = a.nseg[1] = 0;
+    for (const S &sg : segs) {
+        int wi = 0;
+        while (wi < *n_widths && widths[wi] != sg.ncol) ++wi;
+        if (wi == *n_widths) widths[(*n_widths)++] = sg.ncol;
+        const int g = load[1] < load[0] ? 1 : 0;
+        ConvSeg &d = a.seg[g][a.nseg[g]++];
+        d.col0 = (int16_t)sg.col0; d.ncol = (int16_t)sg.ncol; d.chan = sg.chan; d.map = (int16_t)wi;
+        d.swz = (int16_t)(sg.ncol == 64 ? 7 : (sg.ncol == 32 ? 3 : (sg.ncol == 16 ? 1 : 0)));
+        load[g] += sg.ncol;
+    }
+}
+
 // Fill the shape-dependent ConvArgs + tensor maps of one CONV / DETECT op.
 int bind_conv(ry_plan *p, Op &op, std::vector<CUtensorMap> &maps) {
     const ry_op_desc &d = op.d;
@@ -186,15 +225,17 @@ int bind_conv(ry_plan *p, Op &op, std::vector<CUtensorMap> &maps) {
     if (s != 1 && !(s == 2 && k == 3)) RY_FAIL("conv: only 1x1 s1, 3x3 s1 and 3x3 s2 are built");
     ConvArgs &a = op.ca;
     memset(&a, 0, sizeof(a));
-    a.kb = cp.kb; a.cblk = cp.cblk; a.ntaps = cp.ntaps; a.kblocks = cp.ntaps * cp.cblk;
-    a.BN = cp.BN; a.n_ntiles = cp.n_ntiles;
-    a.stages = conv_pick_stages(cp.BN);
+    a.kb = cp.kb; a.cblk = cp.cblk; a.ntaps = cp.ntaps; a.kblocks = cp.ntaps * cp.cblk; a.ksteps_last = cp.ksteps_last;
+    a.BN = cp.BN; a.n_ntiles = cp.n_ntiles; a.cout_pad = cp.cout_pad;
     a.img_w = Wo; a.img_hw = Ho * Wo;
+    a.mode = d.kind == RY_OP_DETECT ? 1 : 0;
     op.tmap_first = (int)maps.size();
     const size_t esz = 2;
     const cuuint64_t ctot = (cuuint64_t)tin.d.channels;
     __nv_bfloat16 *in_base = bf(p, d.in0.tensor) + d.in0.c_off;
+    static const bool no_halo = getenv("RY_CONV_NO_HALO") != nullptr;
     CUtensorMap m;
+    a.a_mode = A_BOX;
     if (k == 1) {
         const cuuint64_t P = (cuuint64_t)B * Hi * Wi;
         a.tw = 128; a.th = 1; a.tn = 1;
@@ -205,6 +246,17 @@ int bind_conv(ry_plan *p, Op &op, std::vector<CUtensorMap> &maps) {
         if (encode_map(&m, in_base, 4, dims, str, box, cp.kb)) return 1;
         maps.push_back(m);
         a.tap_map[0] = 0; a.tap_dh[0] = 0; a.tap_dw[0] = 0;
+    } else if (s == 1 && !no_halo && Wo % kHaloTw == 0 && Ho % kHaloTh == 0) {
+        // halo mode: one (8+2) x (16+2) pixel box per K block, the nine taps are descriptor windows into it
+        a.a_mode = A_HALO;
+        a.tw = kHaloTw; a.th = kHaloTh; a.tn = 1;
+        a.halo_w = kHaloTw + 2;
+        a.Wo = Wo; a.Ho = Ho; a.Bo = B;
+        const cuuint64_t dims[4] = {(cuuint64_t)d.cin, (cuuint64_t)Wi, (cuuint64_t)Hi, (cuuint64_t)B};
+        const cuuint64_t str[3] = {ctot * esz, (cuuint64_t)Wi * ctot * esz, (cuuint64_t)Hi * Wi * ctot * esz};
+        const cuuint32_t box[4] = {(cuuint32_t)cp.kb, (cuuint32_t)(kHaloTw + 2), (cuuint32_t)(kHaloTh + 2), 1};
+        if (encode_map(&m, in_base, 4, dims, str, box, cp.kb)) return 1;
+        maps.push_back(m);
     } else {
         pick_tile(B, Ho, Wo, &a.tw, &a.th, &a.tn);
         a.Wo = Wo; a.Ho = Ho; a.Bo = B;
@@ -234,6 +286,7 @@ int bind_conv(ry_plan *p, Op &op, std::vector<CUtensorMap> &maps) {
             }
         }
     }
+    op.n_amaps = (int)maps.size() - op.tmap_first;
     a.tiles_w = cdiv(a.Wo, a.tw); a.tiles_h = cdiv(a.Ho, a.th); a.tiles_n = cdiv(a.Bo, a.tn);
     {   // weights: [cout_pad][k_pad]
         const cuuint64_t dims[2] = {(cuuint64_t)cp.k_pad, (cuuint64_t)cp.cout_pad};
@@ -249,26 +302,55 @@ int bind_conv(ry_plan *p, Op &op, std::vector<CUtensorMap> &maps) {
     op.grid = (int)std::min<long>(tiles, kNumSMs);
     op.launches = 1;
     if (d.kind == RY_OP_DETECT) {
-        a.mode = 1;
         a.no = p->nc + 5;
         a.na = d.cout / a.no;
         a.det_stride = d.fparam[0];
         for (int i = 0; i < 6; ++i) a.anchors[i] = d.fparam[1 + i];
-        a.split_at = 1 << 30;
+        if (cp.BN != 32) RY_FAIL("detect: na*(nc+5) must be in (16, 32] for the fused decode epilogue");
+        if (conv_plan_smem(a, 8)) RY_FAIL("detect: shared memory plan failed");
         return 0;
     }
-    a.mode = 0;
     const Tensor &tout = p->tensors[d.out0.tensor];
     if (tout.h != Ho || tout.w != Wo) RY_FAIL("conv: output tensor level does not match stride");
-    a.out = bf(p, d.out0.tensor);
-    a.out_cs = tout.d.channels;
-    a.off0 = d.out0.c_off;
+    if (d.cout % 8 != 0) RY_FAIL("conv: cout must be a multiple of 8");
+    OutPiece pieces[2];
+    int n_pieces = 1;
+    cuuint64_t c_end = (cuuint64_t)tout.d.channels;
     if (d.out1.tensor >= 0) {
-        if (d.out1.tensor != d.out0.tensor || d.out0.c_len % 16 != 0) RY_FAIL("conv: bad split store");
-        a.split_at = d.out0.c_len;
-        a.off1 = d.out1.c_off;
+        if (d.out1.tensor != d.out0.tensor || cp.n_ntiles != 1 || d.out0.c_len + d.out1.c_len != d.cout) RY_FAIL("conv: bad split store");
+        pieces[0] = {0, d.out0.c_len, d.out0.c_off};
+        pieces[1] = {d.out0.c_len, d.out1.c_len, d.out1.c_off};
+        n_pieces = 2;
+    } else if (cp.n_ntiles == 1) {
+        pieces[0] = {0, d.cout, d.out0.c_off};
     } else {
-        a.split_at = 1 << 30;
+        pieces[0] = {0, cp.BN, d.out0.c_off};                       // per N tile; channels past the view are clipped by the map
+        c_end = (cuuint64_t)(d.out0.c_off + d.out0.c_len);
+    }
+    int widths[4], n_widths = 0;
+    int max_cols = 64;
+    build_segments(a, pieces, n_pieces, max_cols, widths, &n_widths);
+    if (conv_plan_smem(a, widths[0])) RY_FAIL("conv: shared memory plan failed");
+    if (!a.b_resident && a.a_mode == A_BOX && a.a_stages < 4 && widths[0] > 32) {   // big tiles: trade staging for pipeline depth
+        build_segments(a, pieces, n_pieces, 32, widths, &n_widths);
+        if (conv_plan_smem(a, widths[0])) RY_FAIL("conv: shared memory plan failed");
+    }
+    if (a.nseg[0] > kConvMaxSegs || a.nseg[1] > kConvMaxSegs) RY_FAIL("conv: too many store segments");
+    for (int wi = 0; wi < n_widths; ++wi) {
+        const cuuint64_t oc = (cuuint64_t)tout.d.channels;
+        if (k == 1) {
+            const cuuint64_t P = (cuuint64_t)a.Wo;
+            const cuuint64_t dims[4] = {c_end, P, 1, 1};
+            const cuuint64_t str[3] = {oc * esz, P * oc * esz, P * oc * esz};
+            const cuuint32_t box[4] = {(cuuint32_t)widths[wi], 128, 1, 1};
+            if (encode_map(&m, bf(p, d.out0.tensor), 4, dims, str, box, widths[wi])) return 1;
+        } else {
+            const cuuint64_t dims[4] = {c_end, (cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)B};
+            const cuuint64_t str[3] = {oc * esz, (cuuint64_t)Wo * oc * esz, (cuuint64_t)Ho * Wo * oc * esz};
+            const cuuint32_t box[4] = {(cuuint32_t)widths[wi], (cuuint32_t)a.tw, (cuuint32_t)a.th, (cuuint32_t)a.tn};
+            if (encode_map(&m, bf(p, d.out0.tensor), 4, dims, str, box, widths[wi])) return 1;
+        }
+        maps.push_back(m);
     }
     if (d.in1.tensor >= 0) {
         a.res = bf(p, d.in1.tensor);
@@ -298,7 +380,8 @@ int run_op(ry_plan *p, Op &op, const float *image, float *pred, float *raws[3], 
         case RY_OP_CONV: {
             ConvArgs a = op.ca;
             a.amap = p->d_tmaps + op.tmap_first;
-            a.wmap = p->d_tmaps + op.tmap_first + (d.stride == 2 ? 4 : 1);
+            a.wmap = a.amap + op.n_amaps;
+            a.omap = a.wmap + 1;
             conv_launch(a, op.grid, st);
             break;
         }
@@ -306,7 +389,8 @@ int run_op(ry_plan *p, Op &op, const float *image, float *pred, float *raws[3], 
             if (!pred) RY_FAIL("detect: pred pointer is NULL");
             ConvArgs a = op.ca;
             a.amap = p->d_tmaps + op.tmap_first;
-            a.wmap = p->d_tmaps + op.tmap_first + 1;
+            a.wmap = a.amap + op.n_amaps;
+            a.omap = a.wmap;
             a.pred = pred;
             a.raw = raws[d.level_idx];
             conv_launch(a, op.grid, st);
