@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const __grid
         }
         for (int a = 0; a < 2; ++a) {
             ptx::mbar_init(tfull + a, 1);
-            ptx::mbar_init(tempty + a, 8);
+            ptx::mbar_init(tempty + a, p.ep_teams ? 4 : 8);
         }
         ptx::mbar_init(bres, 1);
         ptx::fence_mbar_init();
@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const __grid
     } else if (warp == 1) {
         // ===================== MMA issuer (whole warp in uniform control flow, one elected lane issues) =============
         // Descriptors are built once; per stage / tap / K step only their low word (start address >> 4) moves.
-        const bool issuer = ptx::elect_one();
+        const uint32_t issue = ptx::elect_one() ? 1u : 0u;
         const uint32_t idesc = ptx::umma_idesc_bf16(128, p.BN);
         const uint32_t a_sbo = (p.a_mode == A_HALO ? p.halo_w : 8) * rb;
         const uint64_t a_desc0 = ptx::umma_smem_desc(ptx::smem_u32(sA), rb, a_sbo);
@@ -215,6 +215,14 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const __grid
         }
         int sa = 0, sb = 0, acc = 0;
         uint32_t pha = 0, phb = 0, aph = 0;
+        // one tap / K block: `ks` K=16 steps; the first one takes the run-time accumulate flag
+#define RY_MMA_BLOCK(A_LO, B_LO, FIRST_ACC)                                                                   \
+        do {                                                                                                  \
+            ptx::umma_bf16_first(d_tmem, (A_LO), a_hi, (B_LO), b_hi, idesc, issue, (FIRST_ACC));              \
+            if (ks > 1) ptx::umma_bf16_k<2, 1>(d_tmem, (A_LO), a_hi, (B_LO), b_hi, idesc, issue);             \
+            if (ks > 2) ptx::umma_bf16_k<4, 1>(d_tmem, (A_LO), a_hi, (B_LO), b_hi, idesc, issue);             \
+            if (ks > 3) ptx::umma_bf16_k<6, 1>(d_tmem, (A_LO), a_hi, (B_LO), b_hi, idesc, issue);             \
+        } while (0)
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
             ptx::mbar_wait(tempty + acc, aph ^ 1);
             ptx::tc_fence_after();
@@ -240,23 +248,16 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const __grid
                             } else {
                                 b_lo = b_lo0 + b_idx * b_inc;
                             }
-                            if (issuer) {
-                                const uint32_t a_t = a_row + tw * pix_inc;
-#pragma unroll
-                                for (int k = 0; k < 4; ++k) {
-                                    if (k < ks) {
-                                        ptx::umma_bf16_lohi(d_tmem, a_t + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc, accumulate);
-                                        accumulate = 1;
-                                    }
-                                }
-                                if (stream_b) ptx::umma_commit(emptyB + sb);
+                            RY_MMA_BLOCK(a_row + tw * pix_inc, b_lo, accumulate);
+                            accumulate = 1;
+                            if (stream_b) {
+                                ptx::umma_commit_pred(emptyB + sb, issue);
+                                if (++sb == p.b_stages) { sb = 0; phb ^= 1; }
                             }
-                            if (stream_b && ++sb == p.b_stages) { sb = 0; phb ^= 1; }
                             b_idx += p.cblk;
                         }
                         a_row += row_inc;
                     }
-                    accumulate = 1;
                 } else {
                     uint32_t b_lo;
                     if (stream_b) {
@@ -266,26 +267,21 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const __grid
                     } else {
                         b_lo = b_lo0 + ia * b_inc;
                     }
-                    if (issuer) {
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            if (k < ks) {
-                                ptx::umma_bf16_lohi(d_tmem, a_lo + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc, accumulate);
-                                accumulate = 1;
-                            }
-                        }
-                        if (stream_b) ptx::umma_commit(emptyB + sb);
-                    }
+                    RY_MMA_BLOCK(a_lo, b_lo, accumulate);
                     accumulate = 1;
-                    if (stream_b && ++sb == p.b_stages) { sb = 0; phb ^= 1; }
+                    if (stream_b) {
+                        ptx::umma_commit_pred(emptyB + sb, issue);
+                        if (++sb == p.b_stages) { sb = 0; phb ^= 1; }
+                    }
                 }
-                if (issuer) ptx::umma_commit(emptyA + sa);    // frees the A stage once these MMAs retire
+                ptx::umma_commit_pred(emptyA + sa, issue);    // frees the A stage once these MMAs retire
                 if (++sa == p.a_stages) { sa = 0; pha ^= 1; }
                 if (++c == p.cblk) c = 0;
             }
-            if (issuer) ptx::umma_commit(tfull + acc);        // accumulator ready for the epilogue
+            ptx::umma_commit_pred(tfull + acc, issue);        // accumulator ready for the epilogue
             if (++acc == 2) { acc = 0; aph ^= 1; }
         }
+#undef RY_MMA_BLOCK
         __syncwarp();
     } else {
         // ===================== epilogue: 2 column groups x 4 warps (TMEM lane quarter = warp % 4) =====================
@@ -297,9 +293,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const __grid
         const int w_in = row % p.tw, h_in = (row / p.tw) % p.th, n_in = row / (p.tw * p.th);
         const float scale = p.act == 1 ? 0.5f : 1.0f;
         const uint32_t stage_u = ptx::smem_u32(sStage) + grp * 2 * p.stage_buf_bytes;
-        int acc = 0, bufsel = 0;
-        uint32_t aph = 0;
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int bufsel = 0, it = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+            if (p.ep_teams && (it & 1) != grp) continue;          // tile teams: this team's tiles use accumulator `grp`
+            const int acc = it & 1;
+            const uint32_t aph = (uint32_t)(it >> 1) & 1u;
             const TileCoord tc = tile_coord(p, t);
             const int w = tc.w0 + w_in, h = tc.h0 + h_in, n = tc.n0 + n_in;
             const bool valid = (n_in < p.tn) && (w < p.Wo) && (h < p.Ho) && (n < p.Bo);
@@ -356,7 +354,6 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const __grid
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(tempty + acc);
-            if (++acc == 2) { acc = 0; aph ^= 1; }
         }
         if (leader) ptx::bulk_wait_read<0>();                       // staging must outlive the last TMA store's read
     }

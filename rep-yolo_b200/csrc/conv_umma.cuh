@@ -34,10 +34,10 @@ constexpr int kHaloTw = 8, kHaloTh = 16;
 enum { A_BOX = 0, A_HALO = 1 };
 
 struct ConvSeg {
-    int16_t col0, ncol;      // accumulator columns [col0, col0+ncol) of the N tile; ncol in {8, 16, 32, 64}
+    int16_t col0, ncol;      // accumulator columns [col0, col0+ncol) of the N tile; ncol <= 64, multiple of 8
     int32_t chan;            // absolute channel in the output tensor (n-tile offset added at run time)
     int16_t map;             // index into omap[]
-    int16_t swz;             // XOR mask of the staging layout: 7 / 3 / 1 / 0 for 128 / 64 / 32 / 16-byte rows
+    int16_t swz;             // XOR mask of the staging layout: 7 / 3 / 1 for 128 / 64 / 32-byte rows, 0 = dense rows
 };
 
 struct ConvArgs {
@@ -61,6 +61,7 @@ struct ConvArgs {
     int b_stage_bytes, b_stages, b_resident;
     int stage_buf_bytes;       // epilogue staging: 2 groups x 2 buffers of this size
     int mode;                  // 0 = bf16 NHWC store, 1 = Detect decode
+    int ep_teams;              // 1: the two 4-warp epilogue groups take alternate TILES (small N); 0: disjoint COLUMNS of each tile
     const float *bias;         // [Cout_pad]
     int cout, cout_pad;
     int act;

@@ -188,18 +188,25 @@ struct OutPiece { int col0, len, chan; };
 void build_segments(ConvArgs &a, const OutPiece *pieces, int n_pieces, int max_cols, int widths[4], int *n_widths) {
     int total = 0;
     for (int i = 0; i < n_pieces; ++i) total += pieces[i].len;
-    int wmax = 8;
-    while (wmax * 2 <= max_cols && wmax * 2 <= std::max(8, total / 2)) wmax *= 2;
     struct S { int col0, ncol, chan; };
     std::vector<S> segs;
-    for (int i = 0; i < n_pieces; ++i)
-        for (int c = 0; c < pieces[i].len;) {
-            int w = wmax;
-            while (w > pieces[i].len - c) w /= 2;
-            segs.push_back({pieces[i].col0 + c, w, pieces[i].chan + c});
-            c += w;
-        }
-    std::stable_sort(segs.begin(), segs.end(), [](const S &x, const S &y) { return x.ncol > y.ncol; });
+    // small N: one segment per output piece (dense rows unless the width is a power of two), the two epilogue groups work
+    // as teams on alternate tiles; otherwise power-of-two segments spread over two column groups
+    a.ep_teams = (total <= 64 && n_pieces <= kConvMaxSegs) ? 1 : 0;
+    if (a.ep_teams) {
+        for (int i = 0; i < n_pieces; ++i) segs.push_back({pieces[i].col0, pieces[i].len, pieces[i].chan});
+    } else {
+        int wmax = 8;
+        while (wmax * 2 <= max_cols && wmax * 2 <= std::max(8, total / 2)) wmax *= 2;
+        for (int i = 0; i < n_pieces; ++i)
+            for (int c = 0; c < pieces[i].len;) {
+                int w = wmax;
+                while (w > pieces[i].len - c) w /= 2;
+                segs.push_back({pieces[i].col0 + c, w, pieces[i].chan + c});
+                c += w;
+            }
+        std::stable_sort(segs.begin(), segs.end(), [](const S &x, const S &y) { return x.ncol > y.ncol; });
+    }
     *n_widths = 0;
     int load[2] = {0, 0};
     a.nseg[0] = a.nseg[1] = 0;
@@ -207,11 +214,14 @@ void build_segments(ConvArgs &a, const OutPiece *pieces, int n_pieces, int max_c
         int wi = 0;
         while (wi < *n_widths && widths[wi] != sg.ncol) ++wi;
         if (wi == *n_widths) widths[(*n_widths)++] = sg.ncol;
-        const int g = load[1] < load[0] ? 1 : 0;
-        ConvSeg &d = a.seg[g][a.nseg[g]++];
-        d.col0 = (int16_t)sg.col0; d.ncol = (int16_t)sg.ncol; d.chan = sg.chan; d.map = (int16_t)wi;
-        d.swz = (int16_t)(sg.ncol == 64 ? 7 : (sg.ncol == 32 ? 3 : (sg.ncol == 16 ? 1 : 0)));
-        load[g] += sg.ncol;
+        for (int g = 0; g < 2; ++g) {
+            if (!a.ep_teams && g != (load[1] < load[0] ? 1 : 0)) continue;
+            ConvSeg &d = a.seg[g][a.nseg[g]++];
+            d.col0 = (int16_t)sg.col0; d.ncol = (int16_t)sg.ncol; d.chan = sg.chan; d.map = (int16_t)wi;
+            d.swz = (int16_t)(sg.ncol == 64 ? 7 : (sg.ncol == 32 ? 3 : (sg.ncol == 16 ? 1 : 0)));
+            load[g] += sg.ncol;
+            if (!a.ep_teams) break;
+        }
     }
 }
 
@@ -330,10 +340,10 @@ int bind_conv(ry_plan *p, Op &op, std::vector<CUtensorMap> &maps) {
     int widths[4], n_widths = 0;
     int max_cols = 64;
     build_segments(a, pieces, n_pieces, max_cols, widths, &n_widths);
-    if (conv_plan_smem(a, widths[0])) RY_FAIL("conv: shared memory plan failed");
-    if (!a.b_resident && a.a_mode == A_BOX && a.a_stages < 4 && widths[0] > 32) {   // big tiles: trade staging for pipeline depth
+    if (conv_plan_smem(a, *std::max_element(widths, widths + n_widths))) RY_FAIL("conv: shared memory plan failed");
+    if (!a.ep_teams && !a.b_resident && a.a_mode == A_BOX && a.a_stages < 4 && widths[0] > 32) {   // big tiles: trade staging for pipeline depth
         build_segments(a, pieces, n_pieces, 32, widths, &n_widths);
-        if (conv_plan_smem(a, widths[0])) RY_FAIL("conv: shared memory plan failed");
+        if (conv_plan_smem(a, *std::max_element(widths, widths + n_widths))) RY_FAIL("conv: shared memory plan failed");
     }
     if (a.nseg[0] > kConvMaxSegs || a.nseg[1] > kConvMaxSegs) RY_FAIL("conv: too many store segments");
     for (int wi = 0; wi < n_widths; ++wi) {

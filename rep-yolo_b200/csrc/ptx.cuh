@@ -137,6 +137,52 @@ __device__ __forceinline__ void umma_bf16_lohi(uint32_t d_tmem, uint32_t a_lo, u
         "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// Predicated forms for a warp that stays in uniform control flow: every lane executes the statement, `issue` is true in
+// the one elected lane.  Descriptors are (lo, hi) words; `koff` = K-step byte offset >> 4 folded in as an immediate.
+template <int KOFF, int ACC>
+__device__ __forceinline__ void umma_bf16_k(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                            uint32_t idesc, uint32_t issue) {
+    asm volatile(
+        "{\n"
+        ".reg .pred q;\n"
+        ".reg .b32 al, bl;\n"
+        ".reg .b64 da, db;\n"
+        "setp.ne.b32 q, %6, 0;\n"
+        "add.u32 al, %1, %7;\n"
+        "add.u32 bl, %3, %7;\n"
+        "mov.b64 da, {al, %2};\n"
+        "mov.b64 db, {bl, %4};\n"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, %8;\n"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(issue), "n"(KOFF), "n"(ACC)
+        : "memory");
+}
+// accumulate flag in a register (first MMA of a tile)
+__device__ __forceinline__ void umma_bf16_first(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                                uint32_t idesc, uint32_t issue, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred q, p;\n"
+        ".reg .b64 da, db;\n"
+        "setp.ne.b32 q, %6, 0;\n"
+        "setp.ne.b32 p, %7, 0;\n"
+        "mov.b64 da, {%1, %2};\n"
+        "mov.b64 db, {%3, %4};\n"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(issue), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_pred(uint64_t *bar, uint32_t issue) {
+    asm volatile(
+        "{\n"
+        ".reg .pred q;\n"
+        "setp.ne.b32 q, %1, 0;\n"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(issue)
+        : "memory");
+}
 // Arrives on the mbarrier when all previously issued MMAs of this thread have completed (implies fence::before).
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
