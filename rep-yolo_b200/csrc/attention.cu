@@ -4,13 +4,18 @@
 //                have 8 input channels per output channel (DWConv(c, c/8): groups = c/8, common.py:154-156).
 //  crisscross  : eH[h,w,g] = q[h,w].k[g,w], eW[h,w,g] = q[h,w].k[h,g]; softmax over the H+W energies (no -inf diagonal);
 //                out = sum_g v[g,w] aH + sum_g v[h,g] aW; gamma*out + x                     (common.py:3704-3726)
-//                Done as two "line attention" passes that are merged like a split soft-max:
+//                Two "line attention" passes merged like a split soft-max:
 //                  row pass  (CTA = one image row)    -> un-normalised partial O_W, running max m_W, sum s_W (scratch)
 //                  col pass  (CTA = one image column) -> O_H, m_H, s_H, merge with the row partials, gamma*out + x
-//  vertical    : out[y,x] = sum_g v[g,x] * (q[x,y].k[g,y])  (raw energies, H == W; common.py:3763-3778)
-//                CTA = one output column x.
+//  vertical    : out[y=j,x=i] = sum_k v[k,i] * (q[i,j].k[k,j])   (raw energies, H == W; common.py:3763-3778)
+//                  energy pass (CTA = image column j): E_j[i][k] = q[i,j].k[k,j]  -> bf16 scratch [b][i][j][k]
+//                  value pass  (CTA = output column i): out[j,i] = E[i][j][:] . v[:,i]; gamma*out + x
 //  v = ReLU6(bn1(SiLU(wv*x + bv))) is recomputed from x where needed (depthwise 1x1: purely per element).
-// All arithmetic is fp32 on bf16 inputs; the [L x L] . [L x C] product is register-tiled from shared memory.
+//
+// Both matrix products of a line run on the tensor cores (mma.sync m16n8k16, bf16 in / fp32 accumulate; the lines are
+// 20..160 long, far below a tcgen05 tile).  Energies feed a soft-max, so q and k are split into bf16 hi + lo parts and
+// E = Qhi.Khi + Qhi.Klo + Qlo.Khi is ONE contraction over 3*Cq (error ~2^-16 relative, fp32-like); soft-max statistics
+// stay in fp32 registers; P and V enter the second product as bf16.
 #include "memops.cuh"
 
 #include "common.cuh"
@@ -19,10 +24,7 @@ namespace ry {
 
 namespace {
 
-constexpr int kAttnThreads = 256;
-constexpr int kMaxPix = 10;   // query pixels per thread per chunk
-
-enum { MODE_ROW = 0, MODE_COL = 1, MODE_VERT = 2 };
+enum { MODE_ROW = 0, MODE_COL = 1, MODE_VE = 2, MODE_VPV = 3 };
 
 __global__ void __launch_bounds__(256) attn_qk_kernel(const __nv_bfloat16 *__restrict__ x, int x_cs, int x_off, int Cq,
                                                       size_t npix, const float *__restrict__ wq, const float *__restrict__ bq,
@@ -48,155 +50,274 @@ __global__ void __launch_bounds__(256) attn_qk_kernel(const __nv_bfloat16 *__res
     }
 }
 
-// shared memory: Q[L][Cq] | K[L][Cq+1] | V[L][C] | E[L][L+1] | m[L] | s[L]
-template <int MODE>
-__global__ void __launch_bounds__(kAttnThreads) attn_line_kernel(const AttnParams p) {
-    extern __shared__ float sm[];
-    const int L = (MODE == MODE_ROW) ? p.W : p.H;           // line length (MODE_VERT: H == W)
-    const int lines = (MODE == MODE_ROW) ? p.H : p.W;       // lines per image
+// ---- warp-level tensor-core primitives ----
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+                 : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+                 : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16(float *c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+struct Geom {
+    int L, LP, KQ;              // line length, padded to 16, padded 3*Cq contraction length
+    int sq, sv, sp;             // row strides (elements) of Aq/Bk, Vs, Ps
+};
+
+__device__ __forceinline__ float v_of(float x, float wv, float bv, float s1, float t1) {
+    return relu6_f(fmaf(s1, silu_f(fmaf(wv, x, bv)), t1));
+}
+
+// One line per CTA, one 16-row query tile per warp.  NT = LP / 8 (compile time: register arrays).
+template <int MODE, int NT>
+__global__ void __launch_bounds__(NT * 16) attn_mma_kernel(const AttnParams p, const Geom gm) {
+    extern __shared__ __align__(16) uint8_t sm_raw[];
+    constexpr int LP = NT * 8;
+    const int L = gm.L, C = p.C, Cq = p.Cq, KQ = gm.KQ;
+    const int sq = gm.sq, sv = gm.sv, sp = gm.sp;
+    __nv_bfloat16 *Aq = reinterpret_cast<__nv_bfloat16 *>(sm_raw);
+    __nv_bfloat16 *Bk = Aq + (size_t)LP * sq;
+    __nv_bfloat16 *Vs = (MODE == MODE_VPV) ? Aq : Bk + (size_t)LP * sq;      // value pass has no q/k operands
+    __nv_bfloat16 *Ps = (MODE == MODE_VE) ? Vs : Vs + (size_t)LP * sv;        // energy pass has no V / P
+    const int lines = (MODE == MODE_ROW) ? p.H : p.W;
     const int b = blockIdx.x / lines, line = blockIdx.x % lines;
-    const int C = p.C, Cq = p.Cq, EP = L + 1, KP = Cq + 1;   // padded strides: no bank conflicts
-    float *Q = sm, *K = Q + L * Cq, *V = K + ((L * KP + 3) & ~3) + ((4 - ((L * Cq) & 3)) & 3), *E = V + (size_t)L * C, *mrow = E + (size_t)L * EP, *srow = mrow + L;
     const size_t img = (size_t)b * p.H * p.W;
-    // pixel of line position i (values / outputs)
-    auto pix_of = [&](int i) -> size_t {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, t4 = lane & 3;
+    auto pix_of = [&](int i) -> size_t {       // pixel of line position i
         return (MODE == MODE_ROW) ? img + (size_t)line * p.W + i : img + (size_t)i * p.W + line;
     };
-    // ---- stage Q, K (ROW/COL: along the line; VERT: Q = q of image row `line`) and V ----
-    for (int i = threadIdx.x; i < L * Cq; i += blockDim.x) {
-        const int pi = i / Cq, d = i - pi * Cq;
-        if (MODE == MODE_VERT) {
-            Q[i] = __ldg(p.q + (img + (size_t)line * p.W + pi) * Cq + d);
-        } else {
-            const size_t px = pix_of(pi);
-            Q[i] = __ldg(p.q + px * Cq + d);
-            K[pi * KP + d] = __ldg(p.k + px * Cq + d);
-        }
-    }
-    const int vecs = C / 8;
-    for (int i = threadIdx.x; i < L * vecs; i += blockDim.x) {
-        const int pi = i / vecs, c = (i - pi * vecs) * 8;
-        const uint4 u = __ldg(reinterpret_cast<const uint4 *>(p.x + pix_of(pi) * p.x_cs + p.x_off + c));
-        const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-        for (int h = 0; h < 4; ++h) {
-            const float2 f = unpack_bf16x2(uw[h]);
-            const int c0 = c + 2 * h;
-            V[(size_t)pi * C + c0] = relu6_f(fmaf(__ldg(p.s1 + c0), silu_f(fmaf(__ldg(p.wv + c0), f.x, __ldg(p.bv + c0))), __ldg(p.t1 + c0)));
-            V[(size_t)pi * C + c0 + 1] =
-                relu6_f(fmaf(__ldg(p.s1 + c0 + 1), silu_f(fmaf(__ldg(p.wv + c0 + 1), f.y, __ldg(p.bv + c0 + 1))), __ldg(p.t1 + c0 + 1)));
-        }
-    }
-    __syncthreads();
-    // ---- energies E[i][g] ----
-    for (int e = threadIdx.x; e < L * L; e += blockDim.x) {
-        float acc = 0.0f;
-        if (MODE == MODE_VERT) {
-            const int g = e / L, i = e - g * L;            // i fastest: consecutive threads read consecutive pixels of k
-            const float *kp = p.k + (img + (size_t)g * p.W + i) * Cq;
-            for (int d = 0; d < Cq; ++d) acc = fmaf(Q[i * Cq + d], __ldg(kp + d), acc);
-            E[(size_t)i * EP + g] = acc;
-        } else {
-            const int i = e / L, g = e - i * L;
-            for (int d = 0; d < Cq; ++d) acc = fmaf(Q[i * Cq + d], K[g * KP + d], acc);
-            E[(size_t)i * EP + g] = acc;
-        }
-    }
-    __syncthreads();
-    // ---- soft-max statistics per query row (not for VERT: raw energies are used) ----
-    if (MODE != MODE_VERT) {
-        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-        for (int i = warp; i < L; i += nwarps) {
-            float m = -INFINITY;
-            for (int g = lane; g < L; g += 32) m = fmaxf(m, E[(size_t)i * EP + g]);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-            float s = 0.0f;
-            for (int g = lane; g < L; g += 32) {
-                const float pe = __expf(E[(size_t)i * EP + g] - m);
-                E[(size_t)i * EP + g] = pe;
-                s += pe;
+
+    // ---- stage operands ----
+    if (MODE != MODE_VPV) {
+        // Aq row = [Qhi | Qhi | Qlo | 0], Bk row = [Khi | Klo | Khi | 0]  ->  Aq.Bk^T = Qhi.Khi + Qhi.Klo + Qlo.Khi
+        for (int idx = threadIdx.x; idx < LP * KQ; idx += blockDim.x) {
+            const int pi = idx / KQ, col = idx - pi * KQ;
+            float qa = 0.0f, kb = 0.0f;
+            int sec = 3;
+            if (pi < L && col < 3 * Cq) {
+                sec = col / Cq;
+                const int d = col - sec * Cq;
+                const size_t px = pix_of(pi);
+                qa = __ldg(p.q + px * Cq + d);
+                kb = __ldg(p.k + px * Cq + d);
             }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            if (lane == 0) { mrow[i] = m; srow[i] = s; }
+            const __nv_bfloat16 qh = __float2bfloat16_rn(qa), kh = __float2bfloat16_rn(kb);
+            const __nv_bfloat16 ql = __float2bfloat16_rn(qa - __bfloat162float(qh)), kl = __float2bfloat16_rn(kb - __bfloat162float(kh));
+            Aq[(size_t)pi * sq + col] = sec == 2 ? ql : qh;
+            Bk[(size_t)pi * sq + col] = sec == 1 ? kl : kh;
         }
-        __syncthreads();
     }
-    // ---- O[i][c] = sum_g E[i][g] V[g][c]; thread = 4 channels x up to kMaxPix query pixels ----
-    const int ncg = C / 4;                                  // channel groups
-    const int npg = blockDim.x / ncg;                       // pixel groups working in parallel (>= 1 for C <= 1024)
-    const int cg = threadIdx.x % ncg, pg = threadIdx.x / ncg;
-    if (pg < npg) {
-        for (int base = 0; base < L; base += npg * kMaxPix) {
-            float acc[kMaxPix][4];
+    if (MODE != MODE_VE) {
+        const int vecs = C / 8;
+        for (int idx = threadIdx.x; idx < LP * vecs; idx += blockDim.x) {
+            const int pi = idx / vecs, c = (idx - pi * vecs) * 8;
+            uint4 o = make_uint4(0, 0, 0, 0);
+            if (pi < L) {
+                const uint4 u = __ldg(reinterpret_cast<const uint4 *>(p.x + pix_of(pi) * p.x_cs + p.x_off + c));
+                const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
+                uint32_t ow[4];
 #pragma unroll
-            for (int r = 0; r < kMaxPix; ++r) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.0f;
-            for (int g = 0; g < L; ++g) {
-                const float4 v = *reinterpret_cast<const float4 *>(V + (size_t)g * C + cg * 4);
+                for (int h = 0; h < 4; ++h) {
+                    const float2 f = unpack_bf16x2(uw[h]);
+                    const int c0 = c + 2 * h;
+                    ow[h] = pack_bf16x2(v_of(f.x, __ldg(p.wv + c0), __ldg(p.bv + c0), __ldg(p.s1 + c0), __ldg(p.t1 + c0)),
+                                        v_of(f.y, __ldg(p.wv + c0 + 1), __ldg(p.bv + c0 + 1), __ldg(p.s1 + c0 + 1), __ldg(p.t1 + c0 + 1)));
+                }
+                o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+            }
+            *reinterpret_cast<uint4 *>(Vs + (size_t)pi * sv + c) = o;
+        }
+    }
+    if (MODE == MODE_VPV) {
+        // P[j][k] = E[b][i = line][j][k] (bf16 scratch written by the energy pass), rows j >= L are zero
+        const __nv_bfloat16 *E = reinterpret_cast<const __nv_bfloat16 *>(p.scratch) + ((size_t)b * p.H + line) * p.W * LP;
+        const int vecs = LP / 8;
+        for (int idx = threadIdx.x; idx < LP * vecs; idx += blockDim.x) {
+            const int j = idx / vecs, c = (idx - j * vecs) * 8;
+            uint4 o = make_uint4(0, 0, 0, 0);
+            if (j < L) o = __ldg(reinterpret_cast<const uint4 *>(E + (size_t)j * LP + c));
+            *reinterpret_cast<uint4 *>(Ps + (size_t)j * sp + c) = o;
+        }
+    }
+    __syncthreads();
+
+    const int row0 = warp * 16;                                  // this warp's query rows
+    float m_row[2] = {0.0f, 0.0f}, s_row[2] = {1.0f, 1.0f};
+    if (MODE != MODE_VPV) {
+        // ---- E = Aq . Bk^T for rows row0..row0+15, all LP columns ----
+        float e[NT][4];
 #pragma unroll
-                for (int r = 0; r < kMaxPix; ++r) {
-                    const int i = base + pg + r * npg;
-                    const float e = (i < L) ? E[(size_t)i * EP + g] : 0.0f;
-                    acc[r][0] = fmaf(e, v.x, acc[r][0]);
-                    acc[r][1] = fmaf(e, v.y, acc[r][1]);
-                    acc[r][2] = fmaf(e, v.z, acc[r][2]);
-                    acc[r][3] = fmaf(e, v.w, acc[r][3]);
+        for (int nt = 0; nt < NT; ++nt) e[nt][0] = e[nt][1] = e[nt][2] = e[nt][3] = 0.0f;
+        const uint32_t a_base = smem_addr(Aq + (size_t)(row0 + (lane & 15)) * sq + (lane >> 4) * 8);
+        const uint32_t b_base = smem_addr(Bk + (size_t)((lane & 7) + ((lane >> 4) << 3)) * sq + ((lane >> 3) & 1) * 8);
+        for (int kt = 0; kt < KQ / 16; ++kt) {
+            uint32_t a0, a1, a2, a3;
+            ldsm_x4(a_base + kt * 32, a0, a1, a2, a3);
+#pragma unroll
+            for (int np = 0; np < NT / 2; ++np) {
+                uint32_t b0, b1, b2, b3;
+                ldsm_x4(b_base + (uint32_t)(np * 16 * sq * 2) + kt * 32, b0, b1, b2, b3);
+                mma_bf16(e[2 * np], a0, a1, a2, a3, b0, b1);
+                mma_bf16(e[2 * np + 1], a0, a1, a2, a3, b2, b3);
+            }
+        }
+        if (MODE == MODE_VE) {
+            // raw energies -> bf16 scratch [b][i][j = line][k]; padded k columns are exact zeros (zero Bk rows)
+            __nv_bfloat16 *E = reinterpret_cast<__nv_bfloat16 *>(p.scratch);
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const int i = row0 + g + 8 * hh;
+                if (i < L) {
+                    uint32_t *dst = reinterpret_cast<uint32_t *>(E + (((size_t)b * p.H + i) * p.W + line) * LP) + t4;
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) dst[nt * 4] = pack_bf16x2(e[nt][2 * hh], e[nt][2 * hh + 1]);
                 }
             }
+            return;
+        }
+        // ---- soft-max statistics per query row (columns >= L masked), P -> bf16 shared ----
 #pragma unroll
-            for (int r = 0; r < kMaxPix; ++r) {
-                const int i = base + pg + r * npg;
-                if (i >= L) continue;
-                const size_t px = pix_of(i);
-                const int c = cg * 4;
-                if (MODE == MODE_ROW) {
-                    float *sc = p.scratch + px * (C + 4);
-                    *reinterpret_cast<float4 *>(sc + c) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
-                    if (cg == 0) { sc[C] = mrow[i]; sc[C + 1] = srow[i]; }
-                } else {
-                    float o[4] = {acc[r][0], acc[r][1], acc[r][2], acc[r][3]};
+        for (int hh = 0; hh < 2; ++hh) {
+            float m = -INFINITY;
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                const int col = nt * 8 + 2 * t4;
+                if (col < L) m = fmaxf(m, e[nt][2 * hh]);
+                if (col + 1 < L) m = fmaxf(m, e[nt][2 * hh + 1]);
+            }
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+            float s = 0.0f;
+            const int r = row0 + g + 8 * hh;
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                const int col = nt * 8 + 2 * t4;
+                const float p0 = col < L ? __expf(e[nt][2 * hh] - m) : 0.0f;
+                const float p1 = col + 1 < L ? __expf(e[nt][2 * hh + 1] - m) : 0.0f;
+                s += p0 + p1;
+                *reinterpret_cast<uint32_t *>(Ps + (size_t)r * sp + col) = pack_bf16x2(p0, p1);
+            }
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            m_row[hh] = m;
+            s_row[hh] = s;
+        }
+        __syncwarp();
+    }
+
+    // ---- O = P . V in chunks of 32 channels; epilogue per chunk ----
+    const uint32_t pa_base = smem_addr(Ps + (size_t)(row0 + (lane & 15)) * sp + (lane >> 4) * 8);
+    const uint32_t vb_base = smem_addr(Vs + (size_t)((lane & 7) + ((lane >> 3) & 1) * 8) * sv + (lane >> 4) * 8);
+    for (int c0 = 0; c0 < C; c0 += 32) {
+        float o[4][4];
+#pragma unroll
+        for (int ct = 0; ct < 4; ++ct) o[ct][0] = o[ct][1] = o[ct][2] = o[ct][3] = 0.0f;
+#pragma unroll
+        for (int kt = 0; kt < NT / 2; ++kt) {
+            uint32_t a0, a1, a2, a3;
+            ldsm_x4(pa_base + kt * 32, a0, a1, a2, a3);
+#pragma unroll
+            for (int cp = 0; cp < 2; ++cp) {
+                uint32_t b0, b1, b2, b3;
+                ldsm_x4_trans(vb_base + (uint32_t)(kt * 16 * sv * 2) + (uint32_t)((c0 + cp * 16) * 2), b0, b1, b2, b3);
+                mma_bf16(o[2 * cp], a0, a1, a2, a3, b0, b1);
+                mma_bf16(o[2 * cp + 1], a0, a1, a2, a3, b2, b3);
+            }
+        }
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+            const int i = row0 + g + 8 * hh;
+            if (i >= L) continue;
+            const size_t px = pix_of(i);
+            if (MODE == MODE_ROW) {
+                float *sc = p.scratch + px * (C + 4);
+#pragma unroll
+                for (int ct = 0; ct < 4; ++ct)
+                    *reinterpret_cast<float2 *>(sc + c0 + ct * 8 + 2 * t4) = make_float2(o[ct][2 * hh], o[ct][2 * hh + 1]);
+                if (c0 == 0 && t4 == 0) { sc[C] = m_row[hh]; sc[C + 1] = s_row[hh]; }
+            } else {
+                float fh = 1.0f, fw = 0.0f, inv = 1.0f;
+                const float *sc = p.scratch + px * (C + 4);
+                if (MODE == MODE_COL) {
+                    const float mw = sc[C], sw = sc[C + 1], mh = m_row[hh], sh = s_row[hh];
+                    const float m = fmaxf(mh, mw);
+                    fh = __expf(mh - m);
+                    fw = __expf(mw - m);
+                    inv = 1.0f / (sh * fh + sw * fw);
+                }
+#pragma unroll
+                for (int ct = 0; ct < 4; ++ct) {
+                    const int c = c0 + ct * 8 + 2 * t4;
+                    float o0 = o[ct][2 * hh], o1 = o[ct][2 * hh + 1];
                     if (MODE == MODE_COL) {
-                        const float *sc = p.scratch + px * (C + 4);
-                        const float4 ow = *reinterpret_cast<const float4 *>(sc + c);
-                        const float mw = sc[C], sw = sc[C + 1], mh = mrow[i], sh = srow[i];
-                        const float m = fmaxf(mh, mw);
-                        const float fh = __expf(mh - m), fw = __expf(mw - m);
-                        const float inv = 1.0f / (sh * fh + sw * fw);
-                        o[0] = (o[0] * fh + ow.x * fw) * inv;
-                        o[1] = (o[1] * fh + ow.y * fw) * inv;
-                        o[2] = (o[2] * fh + ow.z * fw) * inv;
-                        o[3] = (o[3] * fh + ow.w * fw) * inv;
+                        const float2 ow = *reinterpret_cast<const float2 *>(sc + c);
+                        o0 = (o0 * fh + ow.x * fw) * inv;
+                        o1 = (o1 * fh + ow.y * fw) * inv;
                     }
-                    const uint2 xu = __ldg(reinterpret_cast<const uint2 *>(p.x + px * p.x_cs + p.x_off + c));
-                    const float2 x0 = unpack_bf16x2(xu.x), x1 = unpack_bf16x2(xu.y);
-                    uint2 res;
-                    res.x = pack_bf16x2(fmaf(p.gamma, o[0], x0.x), fmaf(p.gamma, o[1], x0.y));
-                    res.y = pack_bf16x2(fmaf(p.gamma, o[2], x1.x), fmaf(p.gamma, o[3], x1.y));
-                    *reinterpret_cast<uint2 *>(p.out + px * p.out_cs + p.out_off + c) = res;
+                    const float2 xv = unpack_bf16x2(__ldg(reinterpret_cast<const uint32_t *>(p.x + px * p.x_cs + p.x_off + c)));
+                    *reinterpret_cast<uint32_t *>(p.out + px * p.out_cs + p.out_off + c) =
+                        pack_bf16x2(fmaf(p.gamma, o0, xv.x), fmaf(p.gamma, o1, xv.y));
                 }
             }
         }
     }
 }
 
-size_t attn_smem_bytes(int L, int C, int Cq) {
-    return ((size_t)L * (2 * Cq + 1) + 8 + (size_t)L * C + (size_t)L * (L + 1) + 2 * L) * sizeof(float);
+int pick_nt(int L) {
+    static const int opts[] = {2, 4, 6, 8, 10, 12, 16, 20};
+    for (int nt : opts)
+        if (nt * 8 >= L) return nt;
+    return 0;
+}
+
+template <int MODE, int NT>
+int launch_nt(const AttnParams &p, int L, cudaStream_t st) {
+    Geom gm;
+    gm.L = L;
+    gm.LP = NT * 8;
+    gm.KQ = (3 * p.Cq + 15) / 16 * 16;
+    gm.sq = gm.KQ + 8;
+    gm.sv = p.C + 8;
+    gm.sp = gm.LP + 8;
+    size_t smem = 0;
+    if (MODE != MODE_VPV) smem += 2 * (size_t)gm.LP * gm.sq * 2;
+    if (MODE != MODE_VE) smem += (size_t)gm.LP * gm.sv * 2 + (size_t)gm.LP * gm.sp * 2;
+    if (smem > 227 * 1024) return 1;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(attn_mma_kernel<MODE, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        attr_set = true;
+    }
+    const int lines = (MODE == MODE_ROW) ? p.H : p.W;
+    attn_mma_kernel<MODE, NT><<<p.B * lines, NT * 16, smem, st>>>(p, gm);
+    return 0;
 }
 
 template <int MODE>
-int launch_line(const AttnParams &p, cudaStream_t st) {
+int launch_mode(const AttnParams &p, cudaStream_t st) {
     const int L = (MODE == MODE_ROW) ? p.W : p.H;
-    const int lines = (MODE == MODE_ROW) ? p.H : p.W;
-    const size_t smem = attn_smem_bytes(L, p.C, p.Cq);
-    if (smem > 227 * 1024 || p.C % 8 != 0 || p.C / 4 > kAttnThreads) return 1;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(attn_line_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        attr_set = true;
+    if (p.C % 32 != 0) return 1;
+    switch (pick_nt(L)) {
+        case 2: return launch_nt<MODE, 2>(p, L, st);
+        case 4: return launch_nt<MODE, 4>(p, L, st);
+        case 6: return launch_nt<MODE, 6>(p, L, st);
+        case 8: return launch_nt<MODE, 8>(p, L, st);
+        case 10: return launch_nt<MODE, 10>(p, L, st);
+        case 12: return launch_nt<MODE, 12>(p, L, st);
+        case 16: return launch_nt<MODE, 16>(p, L, st);
+        case 20: return launch_nt<MODE, 20>(p, L, st);
+        default: return 1;
     }
-    attn_line_kernel<MODE><<<p.B * lines, kAttnThreads, smem, st>>>(p);
-    return 0;
 }
 
 }  // namespace
@@ -211,16 +332,22 @@ void attn_qk_launch(const __nv_bfloat16 *x, int x_cs, int x_off, int C, int Cq, 
     attn_qk_kernel<<<(int)g, 256, 0, st>>>(x, x_cs, x_off, Cq, npix, wq, bq, wk, bk, s, t, q, k);
 }
 
-size_t crisscross_scratch_floats(int B, int H, int W, int C) { return (size_t)B * H * W * (C + 4); }
+// crisscross: [B*H*W][C + 4] fp32 row-pass partials; vertical: [B][H][W][LP] bf16 energies -- one shared region
+size_t attn_scratch_bytes(int B, int H, int W, int C) {
+    const size_t cc = (size_t)B * H * W * (C + 4) * 4;
+    const size_t ve = (size_t)B * H * W * (size_t)(pick_nt(H) * 8) * 2;
+    return cc > ve ? cc : ve;
+}
 
 int crisscross_launch(const AttnParams &p, cudaStream_t st) {
-    if (launch_line<MODE_ROW>(p, st)) return 1;
-    return launch_line<MODE_COL>(p, st);
+    if (launch_mode<MODE_ROW>(p, st)) return 1;
+    return launch_mode<MODE_COL>(p, st);
 }
 
 int vertical_launch(const AttnParams &p, cudaStream_t st) {
     if (p.H != p.W) return 2;   // the reference's view chain scrambles indices for H != W: not built yet
-    return launch_line<MODE_VERT>(p, st);
+    if (launch_mode<MODE_VE>(p, st)) return 1;
+    return launch_mode<MODE_VPV>(p, st);
 }
 
 }  // namespace ry

@@ -478,9 +478,9 @@ size_t tensor_bytes(const Tensor &t, int B, int H, int W) {
 size_t scratch_bytes(const ry_plan *p, int B, int H, int W) {
     size_t m = 0;
     for (const Op &op : p->ops)
-        if (op.d.kind == RY_OP_CRISSCROSS) {
+        if (op.d.kind == RY_OP_CRISSCROSS || op.d.kind == RY_OP_VERTICAL) {
             const Tensor &t = p->tensors[op.d.in0.tensor];
-            m = std::max(m, crisscross_scratch_floats(B, H >> t.d.level, W >> t.d.level, op.d.cin) * 4);
+            m = std::max(m, attn_scratch_bytes(B, H >> t.d.level, W >> t.d.level, op.d.cin));
         }
     return m;
 }
@@ -623,7 +623,7 @@ int ry_plan_bind(ry_plan *p, int B, int H, int W, void *workspace, size_t worksp
         if (op.d.kind == RY_OP_CONV || op.d.kind == RY_OP_DETECT) {
             if (bind_conv(p, op, maps)) return 1;
         }
-        if (op.d.kind == RY_OP_CRISSCROSS) op.launches = 2;
+        if (op.d.kind == RY_OP_CRISSCROSS || op.d.kind == RY_OP_VERTICAL) op.launches = 2;
     }
     // Detect rows: level -> anchor -> y -> x (models/yolo.py:152, 166)
     int rows = 0;
