@@ -17,14 +17,18 @@ struct TileCoord {
     int w0, h0, n0, nc0;
 };
 
+// n / d through the precomputed m = ceil(2^32 / d): exact while n * d < 2^32 (tile counts are < 2^20, d < 2^12)
+__device__ __forceinline__ uint32_t fast_div(uint32_t n, uint32_t m) { return m ? __umulhi(n, m) : n; }
+
 __device__ __forceinline__ TileCoord tile_coord(const ConvArgs &p, int t) {
-    const int nt = t % p.n_ntiles;
-    int m = t / p.n_ntiles;
-    const int wi = m % p.tiles_w;
-    m /= p.tiles_w;
-    const int hi = m % p.tiles_h;
-    const int ni = m / p.tiles_h;
-    return {wi * p.tw, hi * p.th, ni * p.tn, nt * p.BN};
+    uint32_t m = fast_div((uint32_t)t, p.div_nt);
+    const int nt = t - (int)m * p.n_ntiles;
+    uint32_t q = fast_div(m, p.div_tw);
+    const int wi = (int)m - (int)q * p.tiles_w;
+    m = q;
+    q = fast_div(m, p.div_th);
+    const int hi = (int)m - (int)q * p.tiles_h;
+    return {wi * p.tw, hi * p.th, (int)q * p.tn, nt * p.BN};
 }
 
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
@@ -87,6 +91,118 @@ __device__ __forceinline__ void detect_epilogue(const ConvArgs &p, const uint32_
     }
 }
 
+
+struct MmaCtx {
+    uint64_t *fullA, *emptyA, *fullB, *emptyB, *tfull, *tempty, *bres;
+    uint32_t sA_u, sB_u, tmem_base;
+    int total_tiles, n_acc;
+};
+
+// One tap / K block: KS K=16 steps into the same accumulator; the first step takes the run-time accumulate flag.
+template <int KS>
+__device__ __forceinline__ void mma_block(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t issue,
+                                          uint32_t first_acc, int ks) {
+    ptx::umma_bf16_d64_first(d_tmem, a_desc, b_desc, idesc, issue, first_acc);
+    if (KS ? KS > 1 : ks > 1) ptx::umma_bf16_d64<2, 1>(d_tmem, a_desc, b_desc, idesc, issue);
+    if (KS ? KS > 2 : ks > 2) ptx::umma_bf16_d64<4, 1>(d_tmem, a_desc, b_desc, idesc, issue);
+    if (KS ? KS > 3 : ks > 3) ptx::umma_bf16_d64<6, 1>(d_tmem, a_desc, b_desc, idesc, issue);
+}
+
+// MMA issuer role: the whole warp stays in uniform control flow, one elected lane issues (predicated statements).
+// HALO / STREAM_B / KS are compile-time so that the per-tap code is a handful of uniform instructions (the issue rate of
+// this single warp bounds small-N layers).  KS = 0: K steps per block decided at run time (multi-chunk layers).
+template <bool HALO, bool STREAM_B, int KS>
+__device__ __forceinline__ void mma_role(const ConvArgs &p, const MmaCtx &cx) {
+    const uint32_t issue = ptx::elect_one() ? 1u : 0u;
+    const int rb = p.kb * 2;
+    const uint32_t idesc = ptx::umma_idesc_bf16(128, p.BN);
+    const uint32_t a_sbo = (HALO ? p.halo_w : 8) * rb;
+    const uint64_t a_desc0 = ptx::umma_smem_desc(cx.sA_u, rb, a_sbo);
+    const uint64_t b_desc0 = ptx::umma_smem_desc(cx.sB_u, rb, 8 * rb);
+    const uint32_t a_inc = (uint32_t)p.a_stage_bytes >> 4, b_inc = (uint32_t)p.b_stage_bytes >> 4;
+    const uint32_t pix_inc = (uint32_t)rb >> 4;                     // one halo pixel
+    const uint32_t row_inc = (uint32_t)(p.halo_w * rb) >> 4;        // one halo row
+    const int n_a = HALO ? p.cblk : p.kblocks;
+    const int ksteps_full = p.kb / 16;
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, cx.tmem_base, 0);
+    if (!STREAM_B) {
+        ptx::mbar_wait(cx.bres, 0);
+        ptx::tc_fence_after();
+    }
+    int sa = 0, sb = 0, acc = 0;
+    uint32_t pha = 0, phb = 0, aph = 0;
+    for (int t = blockIdx.x; t < cx.total_tiles; t += gridDim.x) {
+        ptx::mbar_wait(cx.tempty + acc, aph ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_u + acc * p.BN;
+        uint32_t accumulate = 0;
+        int c = 0;
+        for (int ia = 0; ia < n_a; ++ia) {
+            const int ks = KS ? KS : ((c == p.cblk - 1) ? p.ksteps_last : ksteps_full);
+            ptx::mbar_wait(cx.fullA + sa, pha);
+            ptx::tc_fence_after();
+            const uint64_t a_desc = a_desc0 + (uint64_t)(sa * a_inc);
+            if (HALO) {
+                uint64_t a_row = a_desc;
+                uint32_t b_idx = c;
+#pragma unroll 1
+                for (int th = 0; th < 3; ++th) {
+#pragma unroll
+                    for (int tw = 0; tw < 3; ++tw) {
+                        uint64_t b_desc;
+                        if (STREAM_B) {
+                            ptx::mbar_wait(cx.fullB + sb, phb);
+                            ptx::tc_fence_after();
+                            b_desc = b_desc0 + (uint64_t)(sb * b_inc);
+                        } else {
+                            b_desc = b_desc0 + (uint64_t)(b_idx * b_inc);
+                        }
+                        mma_block<KS>(d_tmem, a_row + (uint64_t)(tw * pix_inc), b_desc, idesc, issue, accumulate, ks);
+                        accumulate = 1;
+                        if (STREAM_B) {
+                            ptx::umma_commit_pred(cx.emptyB + sb, issue);
+                            if (++sb == p.b_stages) { sb = 0; phb ^= 1; }
+                        }
+                        b_idx += p.cblk;
+                    }
+                    a_row += row_inc;
+                }
+            } else {
+                uint64_t b_desc;
+                if (STREAM_B) {
+                    ptx::mbar_wait(cx.fullB + sb, phb);
+                    ptx::tc_fence_after();
+                    b_desc = b_desc0 + (uint64_t)(sb * b_inc);
+                } else {
+                    b_desc = b_desc0 + (uint64_t)(ia * b_inc);
+                }
+                mma_block<KS>(d_tmem, a_desc, b_desc, idesc, issue, accumulate, ks);
+                accumulate = 1;
+                if (STREAM_B) {
+                    ptx::umma_commit_pred(cx.emptyB + sb, issue);
+                    if (++sb == p.b_stages) { sb = 0; phb ^= 1; }
+                }
+            }
+            ptx::umma_commit_pred(cx.emptyA + sa, issue);    // frees the A stage once these MMAs retire
+            if (++sa == p.a_stages) { sa = 0; pha ^= 1; }
+            if (++c == p.cblk) c = 0;
+        }
+        ptx::umma_commit_pred(cx.tfull + acc, issue);        // accumulator ready for the epilogue
+        if (++acc == cx.n_acc) { acc = 0; aph ^= 1; }
+    }
+}
+
+template <bool HALO, bool STREAM_B>
+__device__ __forceinline__ void mma_role_ks(const ConvArgs &p, const MmaCtx &cx) {
+    const int ks = p.cblk == 1 ? p.ksteps_last : (p.ksteps_last == p.kb / 16 ? p.kb / 16 : 0);   // uniform K steps?
+    switch (ks) {
+        case 2: mma_role<HALO, STREAM_B, 2>(p, cx); break;
+        case 3: mma_role<HALO, STREAM_B, 3>(p, cx); break;
+        case 4: mma_role<HALO, STREAM_B, 4>(p, cx); break;
+        default: mma_role<HALO, STREAM_B, 0>(p, cx); break;
+    }
+}
+
 __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const __grid_constant__ ConvArgs p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -97,15 +213,15 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const __grid
     float *sbias = reinterpret_cast<float *>(sStage + 4 * (size_t)p.stage_buf_bytes);
     uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(sbias) + ((p.cout_pad * 4 + 127) & ~127));
     uint64_t *fullA = bars, *emptyA = fullA + 8, *fullB = emptyA + 8, *emptyB = fullB + 8;
-    uint64_t *tfull = emptyB + 8, *tempty = tfull + 2, *bres = tempty + 2;
+    uint64_t *tfull = emptyB + 8, *tempty = tfull + 4, *bres = tempty + 4;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bres + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rb = p.kb * 2;                                   // bytes per operand row == swizzle span
     const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_ntiles;
-    const int ksteps_full = p.kb / 16;
+    const int n_acc = p.n_acc;                                  // TMEM accumulator stages (MMA runs ahead of the epilogue)
     uint32_t tmem_cols = 32;
-    while (tmem_cols < 2u * p.BN) tmem_cols <<= 1;
+    while (tmem_cols < (uint32_t)(n_acc * p.BN)) tmem_cols <<= 1;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < 8; ++s) {
@@ -114,7 +230,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const __grid
             ptx::mbar_init(fullB + s, 1);
             ptx::mbar_init(emptyB + s, 1);
         }
-        for (int a = 0; a < 2; ++a) {
+        for (int a = 0; a < 4; ++a) {
             ptx::mbar_init(tfull + a, 1);
             ptx::mbar_init(tempty + a, p.ep_teams ? 4 : 8);
         }
@@ -193,95 +309,15 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const __grid
         }
         __syncwarp();
     } else if (warp == 1) {
-        // ===================== MMA issuer (whole warp in uniform control flow, one elected lane issues) =============
-        // Descriptors are built once; per stage / tap / K step only their low word (start address >> 4) moves.
-        const uint32_t issue = ptx::elect_one() ? 1u : 0u;
-        const uint32_t idesc = ptx::umma_idesc_bf16(128, p.BN);
-        const uint32_t a_sbo = (p.a_mode == A_HALO ? p.halo_w : 8) * rb;
-        const uint64_t a_desc0 = ptx::umma_smem_desc(ptx::smem_u32(sA), rb, a_sbo);
-        const uint64_t b_desc0 = ptx::umma_smem_desc(ptx::smem_u32(sB), rb, 8 * rb);
-        const uint32_t a_hi = (uint32_t)(a_desc0 >> 32), b_hi = (uint32_t)(b_desc0 >> 32);
-        const uint32_t a_lo0 = (uint32_t)a_desc0, b_lo0 = (uint32_t)b_desc0;
-        const uint32_t a_inc = (uint32_t)p.a_stage_bytes >> 4, b_inc = (uint32_t)p.b_stage_bytes >> 4;
-        const uint32_t pix_inc = (uint32_t)rb >> 4;                     // one halo pixel
-        const uint32_t row_inc = (uint32_t)(p.halo_w * rb) >> 4;        // one halo row
-        const bool stream_b = !p.b_resident;
-        const bool halo = p.a_mode == A_HALO;
-        const int n_a = halo ? p.cblk : p.kblocks;
-        const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
-        if (p.b_resident) {
-            ptx::mbar_wait(bres, 0);
-            ptx::tc_fence_after();
+        // ===================== MMA issuer =====================
+        MmaCtx cx;
+        cx.fullA = fullA; cx.emptyA = emptyA; cx.fullB = fullB; cx.emptyB = emptyB; cx.tfull = tfull; cx.tempty = tempty; cx.bres = bres;
+        cx.sA_u = ptx::smem_u32(sA); cx.sB_u = ptx::smem_u32(sB); cx.tmem_base = tmem_base; cx.total_tiles = total_tiles; cx.n_acc = n_acc;
+        if (p.a_mode == A_HALO) {
+            if (p.b_resident) mma_role_ks<true, false>(p, cx); else mma_role_ks<true, true>(p, cx);
+        } else {
+            if (p.b_resident) mma_role_ks<false, false>(p, cx); else mma_role_ks<false, true>(p, cx);
         }
-        int sa = 0, sb = 0, acc = 0;
-        uint32_t pha = 0, phb = 0, aph = 0;
-        // one tap / K block: `ks` K=16 steps; the first one takes the run-time accumulate flag
-#define RY_MMA_BLOCK(A_LO, B_LO, FIRST_ACC)                                                                   \
-        do {                                                                                                  \
-            ptx::umma_bf16_first(d_tmem, (A_LO), a_hi, (B_LO), b_hi, idesc, issue, (FIRST_ACC));              \
-            if (ks > 1) ptx::umma_bf16_k<2, 1>(d_tmem, (A_LO), a_hi, (B_LO), b_hi, idesc, issue);             \
-            if (ks > 2) ptx::umma_bf16_k<4, 1>(d_tmem, (A_LO), a_hi, (B_LO), b_hi, idesc, issue);             \
-            if (ks > 3) ptx::umma_bf16_k<6, 1>(d_tmem, (A_LO), a_hi, (B_LO), b_hi, idesc, issue);             \
-        } while (0)
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-            ptx::mbar_wait(tempty + acc, aph ^ 1);
-            ptx::tc_fence_after();
-            const uint32_t d_tmem = tmem_u + acc * p.BN;
-            uint32_t accumulate = 0;
-            int c = 0;
-            for (int ia = 0; ia < n_a; ++ia) {
-                const int ks = (c == p.cblk - 1) ? p.ksteps_last : ksteps_full;
-                ptx::mbar_wait(fullA + sa, pha);
-                ptx::tc_fence_after();
-                const uint32_t a_lo = a_lo0 + sa * a_inc;
-                if (halo) {
-                    uint32_t a_row = a_lo, b_idx = c;
-#pragma unroll 1
-                    for (int th = 0; th < 3; ++th) {
-#pragma unroll
-                        for (int tw = 0; tw < 3; ++tw) {
-                            uint32_t b_lo;
-                            if (stream_b) {
-                                ptx::mbar_wait(fullB + sb, phb);
-                                ptx::tc_fence_after();
-                                b_lo = b_lo0 + sb * b_inc;
-                            } else {
-                                b_lo = b_lo0 + b_idx * b_inc;
-                            }
-                            RY_MMA_BLOCK(a_row + tw * pix_inc, b_lo, accumulate);
-                            accumulate = 1;
-                            if (stream_b) {
-                                ptx::umma_commit_pred(emptyB + sb, issue);
-                                if (++sb == p.b_stages) { sb = 0; phb ^= 1; }
-                            }
-                            b_idx += p.cblk;
-                        }
-                        a_row += row_inc;
-                    }
-                } else {
-                    uint32_t b_lo;
-                    if (stream_b) {
-                        ptx::mbar_wait(fullB + sb, phb);
-                        ptx::tc_fence_after();
-                        b_lo = b_lo0 + sb * b_inc;
-                    } else {
-                        b_lo = b_lo0 + ia * b_inc;
-                    }
-                    RY_MMA_BLOCK(a_lo, b_lo, accumulate);
-                    accumulate = 1;
-                    if (stream_b) {
-                        ptx::umma_commit_pred(emptyB + sb, issue);
-                        if (++sb == p.b_stages) { sb = 0; phb ^= 1; }
-                    }
-                }
-                ptx::umma_commit_pred(emptyA + sa, issue);    // frees the A stage once these MMAs retire
-                if (++sa == p.a_stages) { sa = 0; pha ^= 1; }
-                if (++c == p.cblk) c = 0;
-            }
-            ptx::umma_commit_pred(tfull + acc, issue);        // accumulator ready for the epilogue
-            if (++acc == 2) { acc = 0; aph ^= 1; }
-        }
-#undef RY_MMA_BLOCK
         __syncwarp();
     } else {
         // ===================== epilogue: 2 column groups x 4 warps (TMEM lane quarter = warp % 4) =====================
@@ -292,17 +328,23 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const __grid
         const int row = quarter * 32 + lane;
         const int w_in = row % p.tw, h_in = (row / p.tw) % p.th, n_in = row / (p.tw * p.th);
         const float scale = p.act == 1 ? 0.5f : 1.0f;
+        const bool need_pix = p.mode != 0 || p.res != nullptr || p.bvec != nullptr;
         const uint32_t stage_u = ptx::smem_u32(sStage) + grp * 2 * p.stage_buf_bytes;
         int bufsel = 0, it = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
             if (p.ep_teams && (it & 1) != grp) continue;          // tile teams: this team's tiles use accumulator `grp`
-            const int acc = it & 1;
-            const uint32_t aph = (uint32_t)(it >> 1) & 1u;
+            const int acc = n_acc == 4 ? (it & 3) : (it & 1);
+            const uint32_t aph = (uint32_t)(n_acc == 4 ? (it >> 2) : (it >> 1)) & 1u;
             const TileCoord tc = tile_coord(p, t);
-            const int w = tc.w0 + w_in, h = tc.h0 + h_in, n = tc.n0 + n_in;
-            const bool valid = (n_in < p.tn) && (w < p.Wo) && (h < p.Ho) && (n < p.Bo);
-            const size_t pix = ((size_t)n * p.Ho + h) * p.Wo + w;
-            const int img = (int)(pix / p.img_hw);
+            bool valid = false;
+            size_t pix = 0;
+            int img = 0;
+            if (need_pix) {                                       // pixel coordinates: residual / broadcast add / Detect only
+                const int w = tc.w0 + w_in, h = tc.h0 + h_in, n = tc.n0 + n_in;
+                valid = (n_in < p.tn) && (w < p.Wo) && (h < p.Ho) && (n < p.Bo);
+                pix = ((size_t)n * p.Ho + h) * p.Wo + w;
+                img = (int)(pix / p.img_hw);
+            }
             ptx::mbar_wait(tfull + acc, aph);
             ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + acc * p.BN + ((uint32_t)(quarter * 32) << 16);

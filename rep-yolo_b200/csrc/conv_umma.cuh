@@ -53,12 +53,14 @@ struct ConvArgs {
     int8_t tap_map[kConvMaxTaps], tap_dh[kConvMaxTaps], tap_dw[kConvMaxTaps];
     int tw, th, tn;            // output tile extent in w, h, image
     int tiles_w, tiles_h, tiles_n;
+    uint32_t div_nt, div_tw, div_th;   // ceil(2^32 / d) for d = n_ntiles, tiles_w, tiles_h (0 when d == 1): exact q = umulhi(n, m)
     int n_ntiles, BN;          // output-channel tiling
     int Wo, Ho, Bo;            // logical output extent the tile grid covers (1x1: Wo = B*H*W, Ho = Bo = 1)
     int img_w, img_hw;         // true W and H*W of the output map
     int halo_w;                // pixels per halo row (A_HALO)
     int a_stage_bytes, a_stages, a_box_bytes;
     int b_stage_bytes, b_stages, b_resident;
+    int n_acc;                 // TMEM accumulator stages: 2 or 4 (4 * BN <= 512)
     int stage_buf_bytes;       // epilogue staging: 2 groups x 2 buffers of this size
     int mode;                  // 0 = bf16 NHWC store, 1 = Detect decode
     int ep_teams;              // 1: the two 4-warp epilogue groups take alternate TILES (small N); 0: disjoint COLUMNS of each tile

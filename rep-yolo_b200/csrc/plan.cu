@@ -246,6 +246,7 @@ int bind_conv(ry_plan *p, Op &op, std::vector<CUtensorMap> &maps) {
     static const bool no_halo = getenv("RY_CONV_NO_HALO") != nullptr;
     CUtensorMap m;
     a.a_mode = A_BOX;
+    static const char *acc_env = getenv("RY_CONV_NACC");
     if (k == 1) {
         const cuuint64_t P = (cuuint64_t)B * Hi * Wi;
         a.tw = 128; a.th = 1; a.tn = 1;
@@ -297,7 +298,15 @@ int bind_conv(ry_plan *p, Op &op, std::vector<CUtensorMap> &maps) {
         }
     }
     op.n_amaps = (int)maps.size() - op.tmap_first;
+    a.n_acc = (a.a_mode == A_HALO && 4 * cp.BN <= 512) ? 4 : 2;
+    if (acc_env && atoi(acc_env) == 4 && 4 * cp.BN <= 512) a.n_acc = 4;
+    if (acc_env && atoi(acc_env) == 2) a.n_acc = 2;
     a.tiles_w = cdiv(a.Wo, a.tw); a.tiles_h = cdiv(a.Ho, a.th); a.tiles_n = cdiv(a.Bo, a.tn);
+    {
+        auto magic = [](int d) -> uint32_t { return d <= 1 ? 0u : (uint32_t)(((1ull << 32) + (uint64_t)d - 1) / (uint64_t)d); };
+        a.div_nt = magic(a.n_ntiles); a.div_tw = magic(a.tiles_w); a.div_th = magic(a.tiles_h);
+        if ((long)a.tiles_w * a.tiles_h * a.tiles_n * a.n_ntiles >= (1L << 20)) RY_FAIL("conv: too many tiles for the fast tile decode");
+    }
     {   // weights: [cout_pad][k_pad]
         const cuuint64_t dims[2] = {(cuuint64_t)cp.k_pad, (cuuint64_t)cp.cout_pad};
         const cuuint64_t str[1] = {(cuuint64_t)cp.k_pad * esz};

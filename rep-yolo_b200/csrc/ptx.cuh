@@ -137,6 +137,34 @@ __device__ __forceinline__ void umma_bf16_lohi(uint32_t d_tmem, uint32_t a_lo, u
         "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// 64-bit descriptor form: `KOFF` (K-step byte offset >> 4) is added to both start-address fields inside the statement,
+// so the descriptors stay in one uniform register pair each and no per-MMA moves are needed.
+template <int KOFF, int ACC>
+__device__ __forceinline__ void umma_bf16_d64(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t issue) {
+    asm volatile(
+        "{\n"
+        ".reg .pred q;\n"
+        ".reg .b64 da, db;\n"
+        "setp.ne.b32 q, %4, 0;\n"
+        "add.u64 da, %1, %5;\n"
+        "add.u64 db, %2, %5;\n"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, %6;\n"
+        "}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(issue), "n"(KOFF), "n"(ACC)
+        : "memory");
+}
+__device__ __forceinline__ void umma_bf16_d64_first(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t issue,
+                                                    uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred q, p;\n"
+        "setp.ne.b32 q, %4, 0;\n"
+        "setp.ne.b32 p, %5, 0;\n"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(issue), "r"(accumulate)
+        : "memory");
+}
 // Predicated forms for a warp that stays in uniform control flow: every lane executes the statement, `issue` is true in
 // the one elected lane.  Descriptors are (lo, hi) words; `koff` = K-step byte offset >> 4 folded in as an immediate.
 template <int KOFF, int ACC>
