@@ -4,6 +4,8 @@
 // views so that concatenations never materialise.
 #include "memops.cuh"
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace ry {
@@ -67,54 +69,86 @@ __global__ void __launch_bounds__(128) stem_kernel(const float *__restrict__ img
 // ------------------------------------------------------------------------------------------------------------------
 // Depthwise 5x5 s1 p2 + bias + act  (GSConv.cv2, reference models/common.py:3813, 3817).  Channels come as two halves
 // (in_off0 / in_off1) and go to two halves (out_off0 / out_off1): the GSConv channel shuffle folded into addressing.
-// weights: [25][C] fp32 (tap-major), one thread = 8 channels of one pixel.
+// One CTA = one spatial tile (TH rows x TWP pixels) x 32 channels: the (TH+4) x (TWP+4) halo is staged once in shared
+// memory (each input crosses L1/L2 once instead of 25 times); one thread = 8 channels x a strip of 4 pixels of one row,
+// so every staged vector is reused by up to 5 x 4 taps from registers.  weights: [25][C] fp32 (tap-major).
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) dw5_kernel(const __nv_bfloat16 *__restrict__ in, int in_cs, int in_off0, int in_off1,
-                                                  __nv_bfloat16 *__restrict__ out, int out_cs, int out_off0, int out_off1,
-                                                  const float *__restrict__ w, const float *__restrict__ bias, int C,
-                                                  int half, int B, int H, int W, int act) {
-    const int vecs = C / 8;
-    const size_t total = (size_t)B * H * W * vecs;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int v = (int)(i % vecs);
-        const size_t pix = i / vecs;
-        const int x = (int)(pix % W), y = (int)((pix / W) % H);
-        const size_t img_base = (pix / ((size_t)W * H)) * (size_t)H * W;
-        const int c = v * 8;
+constexpr int kDwThreads = 256;
+constexpr int kDwCv = 4;                       // 8-channel vectors per CTA (32 channels)
+
+__global__ void __launch_bounds__(kDwThreads) dw5_kernel(const __nv_bfloat16 *__restrict__ in, int in_cs, int in_off0, int in_off1,
+                                                         __nv_bfloat16 *__restrict__ out, int out_cs, int out_off0, int out_off1,
+                                                         const float *__restrict__ w, const float *__restrict__ bias, int C,
+                                                         int half, int H, int W, int act, int twp, int th, int tiles_x,
+                                                         int tiles_y) {
+    extern __shared__ __align__(16) uint8_t dw_smem[];
+    const int hw_ = twp + 4;                                   // halo row length in pixels
+    uint4 *tile = reinterpret_cast<uint4 *>(dw_smem);          // [(th+4)][hw_][kDwCv] 16-byte vectors
+    float *sw = reinterpret_cast<float *>(tile + (size_t)(th + 4) * hw_ * kDwCv);   // [25][32]
+    float *sb = sw + 25 * 32;                                  // [32]
+    int bid = blockIdx.x;
+    const int cg = bid % (C / 32); bid /= (C / 32);
+    const int tx = bid % tiles_x; bid /= tiles_x;
+    const int ty = bid % tiles_y;
+    const int b = bid / tiles_y;
+    const int x0 = tx * twp, y0 = ty * th, c0 = cg * 32;
+    for (int i = threadIdx.x; i < 25 * 32; i += kDwThreads) sw[i] = __ldg(w + (i / 32) * C + c0 + (i & 31));
+    if (threadIdx.x < 32) sb[threadIdx.x] = __ldg(bias + c0 + threadIdx.x);
+    const size_t img_base = (size_t)b * H * W;
+    for (int i = threadIdx.x; i < (th + 4) * hw_ * kDwCv; i += kDwThreads) {
+        const int v = i % kDwCv, px = (i / kDwCv) % hw_, py = i / (kDwCv * hw_);
+        const int yy = y0 + py - 2, xx = x0 + px - 2;
+        const int c = c0 + v * 8;
         const int ci = c < half ? in_off0 + c : in_off1 + (c - half);
-        const int co = c < half ? out_off0 + c : out_off1 + (c - half);
-        float acc[8];
-        {
-            const float4 b0 = __ldg(reinterpret_cast<const float4 *>(bias + c));
-            const float4 b1 = __ldg(reinterpret_cast<const float4 *>(bias + c + 4));
-            acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w;
-            acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
+        uint4 u = make_uint4(0, 0, 0, 0);
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) u = ldg16(in + (img_base + (size_t)yy * W + xx) * in_cs + ci);
+        tile[i] = u;
+    }
+    __syncthreads();
+    const int v = threadIdx.x % kDwCv, strip = threadIdx.x / kDwCv;
+    const int strips_x = twp / 4;
+    const int sy = strip / strips_x, sx = (strip - sy * strips_x) * 4;
+    if (sy >= th) return;
+    float acc[4][8];
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[p][k] = sb[v * 8 + k];
+#pragma unroll 1
+    for (int dy = 0; dy < 5; ++dy) {
+        float xin[8][8];
+        const uint4 *row = tile + ((size_t)(sy + dy) * hw_ + sx) * kDwCv + v;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint4 u = row[j * kDwCv];
+            const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
+            xin[j][0] = f0.x; xin[j][1] = f0.y; xin[j][2] = f1.x; xin[j][3] = f1.y;
+            xin[j][4] = f2.x; xin[j][5] = f2.y; xin[j][6] = f3.x; xin[j][7] = f3.y;
         }
 #pragma unroll
-        for (int dy = -2; dy <= 2; ++dy) {
-            const int yy = y + dy;
-            if (yy < 0 || yy >= H) continue;
+        for (int dx = 0; dx < 5; ++dx) {
+            const float4 w0 = *reinterpret_cast<const float4 *>(sw + (dy * 5 + dx) * 32 + v * 8);
+            const float4 w1 = *reinterpret_cast<const float4 *>(sw + (dy * 5 + dx) * 32 + v * 8 + 4);
+            const float wk[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-            for (int dx = -2; dx <= 2; ++dx) {
-                const int xx = x + dx;
-                if (xx < 0 || xx >= W) continue;
-                const uint4 u = ldg16(in + (img_base + (size_t)yy * W + xx) * in_cs + ci);
-                const float *wt = w + ((dy + 2) * 5 + (dx + 2)) * C + c;
-                const float4 w0 = __ldg(reinterpret_cast<const float4 *>(wt));
-                const float4 w1 = __ldg(reinterpret_cast<const float4 *>(wt + 4));
-                const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
-                acc[0] = fmaf(f0.x, w0.x, acc[0]); acc[1] = fmaf(f0.y, w0.y, acc[1]);
-                acc[2] = fmaf(f1.x, w0.z, acc[2]); acc[3] = fmaf(f1.y, w0.w, acc[3]);
-                acc[4] = fmaf(f2.x, w1.x, acc[4]); acc[5] = fmaf(f2.y, w1.y, acc[5]);
-                acc[6] = fmaf(f3.x, w1.z, acc[6]); acc[7] = fmaf(f3.y, w1.w, acc[7]);
-            }
-        }
-        if (act == 1) {
+            for (int p = 0; p < 4; ++p)
 #pragma unroll
-            for (int k = 0; k < 8; ++k) acc[k] = silu_f(acc[k]);
+                for (int k = 0; k < 8; ++k) acc[p][k] = fmaf(xin[p + dx][k], wk[k], acc[p][k]);
         }
-        stg16(out + pix * out_cs + co, make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]),
-                                                  pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7])));
+    }
+    const int y = y0 + sy;
+    if (y >= H) return;
+    const int c = c0 + v * 8;
+    const int co = c < half ? out_off0 + c : out_off1 + (c - half);
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const int x = x0 + sx + p;
+        if (x >= W) break;
+        float r[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) r[k] = act == 1 ? silu_f(acc[p][k]) : acc[p][k];
+        stg16(out + (img_base + (size_t)y * W + x) * out_cs + co,
+              make_uint4(pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]), pack_bf16x2(r[4], r[5]), pack_bf16x2(r[6], r[7])));
     }
 }
 
@@ -135,39 +169,49 @@ __global__ void __launch_bounds__(256) maxpool2_kernel(const __nv_bfloat16 *__re
     }
 }
 
-// SPPCSPC pools (reference models/common.py:279, 286): MaxPool2d(k, 1, k//2) for k = 5, 9, 13 (-inf padding), one read
-// of the 13x13 neighbourhood, three writes at channel offsets of the cv5 input buffer.
+// SPPCSPC pools (reference models/common.py:279, 286): MaxPool2d(k, 1, k//2) for k = 5, 9, 13 (-inf padding).  Max is
+// exact, so 9 = 5 o 5 and 13 = 5 o 5 o 5, and each 5x5 is a row pass followed by a column pass.  One CTA = one image x CH
+// channels held in two shared-memory planes: one read of the map, three writes at channel offsets of the cv5 input.
 __global__ void __launch_bounds__(256) spp_kernel(const __nv_bfloat16 *__restrict__ in, int in_cs, int in_off,
                                                   __nv_bfloat16 *__restrict__ out, int out_cs, int off5, int off9,
-                                                  int off13, int C, int B, int H, int W) {
-    const int vecs = C / 8;
-    const size_t total = (size_t)B * H * W * vecs;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int v = (int)(i % vecs);
-        const size_t pix = i / vecs;
-        const int x = (int)(pix % W), y = (int)((pix / W) % H);
-        const size_t img_base = (pix / ((size_t)W * H)) * (size_t)H * W;
-        const uint4 ctr = ldg16(in + pix * in_cs + in_off + v * 8);
-        uint4 m5 = ctr, m9 = ctr, m13 = ctr;
-        for (int dy = -6; dy <= 6; ++dy) {
-            const int yy = y + dy;
-            if (yy < 0 || yy >= H) continue;
-            const int ady = dy < 0 ? -dy : dy;
-            for (int dx = -6; dx <= 6; ++dx) {
-                const int xx = x + dx;
-                if (xx < 0 || xx >= W) continue;
-                const int adx = dx < 0 ? -dx : dx;
-                const int d = ady > adx ? ady : adx;
-                const uint4 u = ldg16(in + (img_base + (size_t)yy * W + xx) * in_cs + in_off + v * 8);
-                m13 = bf16x8_max(m13, u);
-                if (d <= 4) m9 = bf16x8_max(m9, u);
-                if (d <= 2) m5 = bf16x8_max(m5, u);
+                                                  int off13, int C, int H, int W, int CH) {
+    extern __shared__ __align__(16) uint8_t spp_smem[];
+    const int vecs = CH / 8, HW = H * W, n = HW * vecs;
+    uint4 *A = reinterpret_cast<uint4 *>(spp_smem), *Bf = A + n;
+    const int chunks = C / CH;
+    const int b = blockIdx.x / chunks, c0 = (blockIdx.x % chunks) * CH;
+    const size_t img_base = (size_t)b * HW;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int v = i % vecs, pix = i / vecs;
+        A[i] = ldg16(in + (img_base + pix) * in_cs + in_off + c0 + v * 8);
+    }
+    __syncthreads();
+    const int offs[3] = {off5, off9, off13};
+    for (int pass = 0; pass < 3; ++pass) {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {            // row pass: A -> Bf
+            const int v = i % vecs, pix = i / vecs, x = pix % W;
+            uint4 m = A[i];
+#pragma unroll
+            for (int d = 1; d <= 2; ++d) {
+                if (x - d >= 0) m = bf16x8_max(m, A[i - d * vecs]);
+                if (x + d < W) m = bf16x8_max(m, A[i + d * vecs]);
             }
+            (void)v;
+            Bf[i] = m;
         }
-        __nv_bfloat16 *o = out + pix * out_cs + v * 8;
-        stg16(o + off5, m5);
-        stg16(o + off9, m9);
-        stg16(o + off13, m13);
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {            // column pass: Bf -> A, and out
+            const int v = i % vecs, pix = i / vecs, y = pix / W;
+            uint4 m = Bf[i];
+#pragma unroll
+            for (int d = 1; d <= 2; ++d) {
+                if (y - d >= 0) m = bf16x8_max(m, Bf[i - d * W * vecs]);
+                if (y + d < H) m = bf16x8_max(m, Bf[i + d * W * vecs]);
+            }
+            A[i] = m;
+            stg16(out + (img_base + pix) * out_cs + offs[pass] + c0 + v * 8, m);
+        }
+        __syncthreads();
     }
 }
 
@@ -188,19 +232,21 @@ __global__ void __launch_bounds__(256) upsample2_kernel(const __nv_bfloat16 *__r
 }
 
 // CA (reference models/common.py:3797-3802): p = avgpool(x); out = p * sigmoid(f2(relu(f1(p)))) + p  -> [B, C] fp32.
-// One CTA per image; fp32 accumulation of the mean.
-__global__ void __launch_bounds__(512) ca_kernel(const __nv_bfloat16 *__restrict__ in, int in_cs, int in_off,
-                                                 float *__restrict__ out, int out_cs, int out_off, const float *__restrict__ f1,
-                                                 const float *__restrict__ f2, int C, int HW) {
-    extern __shared__ float sm[];            // [C] mean, [C/16] hidden, [512*8] partials
-    float *mean = sm, *hid = sm + C, *part = hid + C / 16;
-    const int b = blockIdx.x, vecs = C / 8;
-    const int groups = blockDim.x / vecs;    // pixel groups working in parallel
+// Stage 1: kCaSplits CTAs per image each sum a pixel range in fp32 -> partial[B][S][C] (fixed order: deterministic).
+// Stage 2: one CTA per image adds the partials in order, then the two tiny FCs.
+constexpr int kCaSplits = 16;
+
+__global__ void __launch_bounds__(256) ca_partial_kernel(const __nv_bfloat16 *__restrict__ in, int in_cs, int in_off,
+                                                         float *__restrict__ partial, int C, int HW) {
+    extern __shared__ float ca_sm[];         // [256 * 8] partials
+    const int b = blockIdx.x / kCaSplits, sp = blockIdx.x % kCaSplits, vecs = C / 8;
+    const int groups = blockDim.x / vecs;    // pixel groups working in parallel (C <= 2048)
     const int v = threadIdx.x % vecs, g = threadIdx.x / vecs;
+    const int p0 = (int)((long)HW * sp / kCaSplits), p1 = (int)((long)HW * (sp + 1) / kCaSplits);
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (g < groups) {
         const __nv_bfloat16 *base = in + (size_t)b * HW * in_cs + in_off + v * 8;
-        for (int p = g; p < HW; p += groups) {
+        for (int p = p0 + g; p < p1; p += groups) {
             const uint4 u = ldg16(base + (size_t)p * in_cs);
             const float2 f0 = unpack_bf16x2(u.x), f1v = unpack_bf16x2(u.y), f2v = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
             acc[0] += f0.x; acc[1] += f0.y; acc[2] += f1v.x; acc[3] += f1v.y;
@@ -208,20 +254,36 @@ __global__ void __launch_bounds__(512) ca_kernel(const __nv_bfloat16 *__restrict
         }
     }
 #pragma unroll
-    for (int k = 0; k < 8; ++k) part[threadIdx.x * 8 + k] = acc[k];
+    for (int k = 0; k < 8; ++k) ca_sm[threadIdx.x * 8 + k] = acc[k];
     __syncthreads();
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         const int vv = c / 8, k = c % 8;
         float s = 0.0f;
-        for (int gg = 0; gg < groups; ++gg) s += part[(gg * vecs + vv) * 8 + k];
+        for (int gg = 0; gg < groups; ++gg) s += ca_sm[(gg * vecs + vv) * 8 + k];
+        partial[((size_t)b * kCaSplits + sp) * C + c] = s;
+    }
+}
+
+__global__ void __launch_bounds__(256) ca_finish_kernel(const float *__restrict__ partial, float *__restrict__ out, int out_cs,
+                                                        int out_off, const float *__restrict__ f1, const float *__restrict__ f2,
+                                                        int C, int HW) {
+    extern __shared__ float ca_sm[];         // [C] mean, [C/16] hidden
+    float *mean = ca_sm, *hid = ca_sm + C;
+    const int b = blockIdx.x;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float s = 0.0f;
+        for (int sp = 0; sp < kCaSplits; ++sp) s += partial[((size_t)b * kCaSplits + sp) * C + c];
         mean[c] = s / (float)HW;
     }
     __syncthreads();
     const int Ch = C / 16;
-    for (int j = threadIdx.x; j < Ch; j += blockDim.x) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int j = warp; j < Ch; j += nw) {
         float s = 0.0f;
-        for (int c = 0; c < C; ++c) s = fmaf(__ldg(f1 + (size_t)j * C + c), mean[c], s);
-        hid[j] = fmaxf(s, 0.0f);
+        for (int c = lane; c < C; c += 32) s = fmaf(__ldg(f1 + (size_t)j * C + c), mean[c], s);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) hid[j] = fmaxf(s, 0.0f);
     }
     __syncthreads();
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -257,9 +319,26 @@ int stem_launch(const float *img, const float *w27, const float *bias, __nv_bflo
 void dw5_launch(const __nv_bfloat16 *in, int in_cs, int in_off0, int in_off1, __nv_bfloat16 *out, int out_cs, int out_off0,
                 int out_off1, const float *w, const float *bias, int C, int half, int B, int H, int W, int act,
                 cudaStream_t st) {
-    const size_t total = (size_t)B * H * W * (C / 8);
-    dw5_kernel<<<grid_for(total, 256), 256, 0, st>>>(in, in_cs, in_off0, in_off1, out, out_cs, out_off0, out_off1, w, bias,
-                                                     C, half, B, H, W, act);
+    // tile: up to 64 strips of 4 pixels; pick the strip layout that wastes the fewest threads / halo pixels
+    int best_twp = 4, best_th = 1;
+    double best = -1.0;
+    for (int sx = 1; sx <= 16; ++sx) {
+        const int twp = sx * 4, th = std::min(64 / sx, H);
+        if (twp - 3 > W && sx > 1) break;
+        const int tiles = cdiv(W, twp) * cdiv(H, th);
+        const double useful = (double)H * W / ((double)tiles * (th + 4) * (twp + 4));   // output pixels per staged pixel
+        if (useful > best) { best = useful; best_twp = twp; best_th = th; }
+    }
+    const int tiles_x = cdiv(W, best_twp), tiles_y = cdiv(H, best_th);
+    const size_t smem = (size_t)(best_th + 4) * (best_twp + 4) * kDwCv * 16 + (25 * 32 + 32) * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(dw5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        attr_set = true;
+    }
+    dw5_kernel<<<B * tiles_y * tiles_x * (C / 32), kDwThreads, smem, st>>>(in, in_cs, in_off0, in_off1, out, out_cs, out_off0, out_off1,
+                                                                         w, bias, C, half, H, W, act, best_twp, best_th, tiles_x,
+                                                                         tiles_y);
 }
 
 void maxpool2_launch(const __nv_bfloat16 *in, int in_cs, int in_off, __nv_bfloat16 *out, int out_cs, int out_off, int C,
@@ -270,8 +349,15 @@ void maxpool2_launch(const __nv_bfloat16 *in, int in_cs, int in_off, __nv_bfloat
 
 void spp_launch(const __nv_bfloat16 *in, int in_cs, int in_off, __nv_bfloat16 *out, int out_cs, int off5, int off9,
                 int off13, int C, int B, int H, int W, cudaStream_t st) {
-    const size_t total = (size_t)B * H * W * (C / 8);
-    spp_kernel<<<grid_for(total, 256), 256, 0, st>>>(in, in_cs, in_off, out, out_cs, off5, off9, off13, C, B, H, W);
+    int CH = 64;
+    while (CH > 8 && (C % CH != 0 || (size_t)2 * H * W * CH * 2 > 200 * 1024)) CH -= 8;
+    const size_t smem = (size_t)2 * H * W * CH * 2;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(spp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        attr_set = true;
+    }
+    spp_kernel<<<B * (C / CH), 256, smem, st>>>(in, in_cs, in_off, out, out_cs, off5, off9, off13, C, H, W, CH);
 }
 
 void upsample2_launch(const __nv_bfloat16 *in, int in_cs, int in_off, __nv_bfloat16 *out, int out_cs, int out_off, int C,
@@ -280,11 +366,12 @@ void upsample2_launch(const __nv_bfloat16 *in, int in_cs, int in_off, __nv_bfloa
     upsample2_kernel<<<grid_for(total, 256), 256, 0, st>>>(in, in_cs, in_off, out, out_cs, out_off, C, B, H, W);
 }
 
+size_t ca_scratch_bytes(int B, int C) { return (size_t)B * kCaSplits * C * sizeof(float); }
+
 void ca_launch(const __nv_bfloat16 *in, int in_cs, int in_off, float *out, int out_cs, int out_off, const float *f1,
-               const float *f2, int C, int B, int HW, cudaStream_t st) {
-    const int threads = 512;
-    const size_t smem = (size_t)(C + C / 16 + threads * 8) * sizeof(float);
-    ca_kernel<<<B, threads, smem, st>>>(in, in_cs, in_off, out, out_cs, out_off, f1, f2, C, HW);
+               const float *f2, int C, int B, int HW, float *scratch, cudaStream_t st) {
+    ca_partial_kernel<<<B * kCaSplits, 256, 256 * 8 * sizeof(float), st>>>(in, in_cs, in_off, scratch, C, HW);
+    ca_finish_kernel<<<B, 256, (size_t)(C + C / 16) * sizeof(float), st>>>(scratch, out, out_cs, out_off, f1, f2, C, HW);
 }
 
 }  // namespace ry

@@ -17,7 +17,8 @@ void spp_launch(const __nv_bfloat16 *in, int in_cs, int in_off, __nv_bfloat16 *o
 void upsample2_launch(const __nv_bfloat16 *in, int in_cs, int in_off, __nv_bfloat16 *out, int out_cs, int out_off, int C,
                       int B, int H, int W, cudaStream_t st);
 void ca_launch(const __nv_bfloat16 *in, int in_cs, int in_off, float *out, int out_cs, int out_off, const float *f1,
-               const float *f2, int C, int B, int HW, cudaStream_t st);
+               const float *f2, int C, int B, int HW, float *scratch, cudaStream_t st);
+size_t ca_scratch_bytes(int B, int C);   // per-split partial sums
 
 // ---- attention (attention.cu) ----
 struct AttnParams {

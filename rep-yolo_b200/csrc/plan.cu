@@ -446,7 +446,7 @@ int run_op(ry_plan *p, Op &op, const float *image, float *pred, float *raws[3], 
         case RY_OP_CA: {
             const Tensor &ti = p->tensors[d.in0.tensor], &to = p->tensors[d.out0.tensor];
             ca_launch(bf(p, d.in0.tensor), ti.d.channels, d.in0.c_off, f32(p, d.out0.tensor), to.d.channels, d.out0.c_off,
-                      wf(p, op.dev[0]), wf(p, op.dev[1]), d.in0.c_len, B, ti.h * ti.w, st);
+                      wf(p, op.dev[0]), wf(p, op.dev[1]), d.in0.c_len, B, ti.h * ti.w, reinterpret_cast<float *>(p->ws + p->scratch_off), st);
             break;
         }
         case RY_OP_ATTN_QK: {
@@ -490,6 +490,8 @@ size_t scratch_bytes(const ry_plan *p, int B, int H, int W) {
         if (op.d.kind == RY_OP_CRISSCROSS || op.d.kind == RY_OP_VERTICAL) {
             const Tensor &t = p->tensors[op.d.in0.tensor];
             m = std::max(m, attn_scratch_bytes(B, H >> t.d.level, W >> t.d.level, op.d.cin));
+        } else if (op.d.kind == RY_OP_CA) {
+            m = std::max(m, ca_scratch_bytes(B, op.d.cin));
         }
     return m;
 }
@@ -632,7 +634,7 @@ int ry_plan_bind(ry_plan *p, int B, int H, int W, void *workspace, size_t worksp
         if (op.d.kind == RY_OP_CONV || op.d.kind == RY_OP_DETECT) {
             if (bind_conv(p, op, maps)) return 1;
         }
-        if (op.d.kind == RY_OP_CRISSCROSS || op.d.kind == RY_OP_VERTICAL) op.launches = 2;
+        if (op.d.kind == RY_OP_CRISSCROSS || op.d.kind == RY_OP_VERTICAL || op.d.kind == RY_OP_CA) op.launches = 2;
     }
     // Detect rows: level -> anchor -> y -> x (models/yolo.py:152, 166)
     int rows = 0;
