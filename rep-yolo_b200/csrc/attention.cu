@@ -31,6 +31,8 @@ __global__ void __launch_bounds__(256) attn_qk_kernel(const __nv_bfloat16 *__res
                                                       const float *__restrict__ wk, const float *__restrict__ bk,
                                                       const float *__restrict__ s, const float *__restrict__ t,
                                                       float *__restrict__ q, float *__restrict__ k) {
+    pdl_trigger();
+    pdl_wait();
     const size_t total = npix * Cq;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int d = (int)(i % Cq);
@@ -80,6 +82,8 @@ __device__ __forceinline__ float v_of(float x, float wv, float bv, float s1, flo
 // One line per CTA, one 16-row query tile per warp.  NT = LP / 8 (compile time: register arrays).
 template <int MODE, int NT>
 __global__ void __launch_bounds__(NT * 16) attn_mma_kernel(const AttnParams p, const Geom gm) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ __align__(16) uint8_t sm_raw[];
     constexpr int LP = NT * 8;
     const int L = gm.L, C = p.C, Cq = p.Cq, KQ = gm.KQ;
@@ -299,7 +303,7 @@ int launch_nt(const AttnParams &p, int L, cudaStream_t st) {
         attr_set = true;
     }
     const int lines = (MODE == MODE_ROW) ? p.H : p.W;
-    attn_mma_kernel<MODE, NT><<<p.B * lines, NT * 16, smem, st>>>(p, gm);
+    launch_pdl(attn_mma_kernel<MODE, NT>, dim3(p.B * lines), dim3(NT * 16), smem, st, p, gm);
     return 0;
 }
 
@@ -329,7 +333,7 @@ void attn_qk_launch(const __nv_bfloat16 *x, int x_cs, int x_off, int C, int Cq, 
     const size_t total = npix * Cq;
     size_t g = (total + 255) / 256;
     if (g > (size_t)kNumSMs * 16) g = (size_t)kNumSMs * 16;
-    attn_qk_kernel<<<(int)g, 256, 0, st>>>(x, x_cs, x_off, Cq, npix, wq, bq, wk, bk, s, t, q, k);
+    launch_pdl(attn_qk_kernel, dim3((int)g), dim3(256), 0, st, x, x_cs, x_off, Cq, npix, wq, bq, wk, bk, s, t, q, k);
 }
 
 // crisscross: [B*H*W][C + 4] fp32 row-pass partials; vertical: [B][H][W][LP] bf16 energies -- one shared region

@@ -29,6 +29,31 @@ void set_error(const std::string &msg);   // plan.cu
 
 constexpr int kNumSMs = 148;
 
+// ---- programmatic dependent launch (PDL) ----
+// Every kernel of the forward pass is launched with the programmatic-stream-serialization attribute and
+//   * calls pdl_trigger() at its top: the NEXT kernel's CTAs may be scheduled as soon as SM resources free up, so its
+//     prologue (barrier init, TMEM alloc, constant weight loads) overlaps this kernel's tail;
+//   * calls pdl_wait() before it touches anything a previous kernel wrote (waits for full completion + visibility of
+//     the prerequisite grid, so ordering is transitively that of a plain stream).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+
 __host__ __device__ inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
 __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }

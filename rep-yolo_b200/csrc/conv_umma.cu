@@ -252,6 +252,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const __grid
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_trigger();                  // the next kernel may start its prologue on SMs this grid has left
 
     if (warp == 0) {
         // ===================== TMA producer (whole warp in uniform control flow, one elected lane issues) ==========
@@ -264,6 +265,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const __grid
         int sa = 0, sb = 0;
         uint32_t pha = 0, phb = 0;
         const bool stream_b = !p.b_resident;
+        pdl_wait();                 // activations are written by earlier kernels (weights above are constants)
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
             const TileCoord tc = tile_coord(p, t);
             if (p.a_mode == A_HALO) {
@@ -331,6 +333,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const __grid
         const bool need_pix = p.mode != 0 || p.res != nullptr || p.bvec != nullptr;
         const uint32_t stage_u = ptx::smem_u32(sStage) + grp * 2 * p.stage_buf_bytes;
         int bufsel = 0, it = 0;
+        pdl_wait();                 // residual / per-image vector reads and all output writes come after the prerequisites
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
             if (p.ep_teams && (it & 1) != grp) continue;          // tile teams: this team's tiles use accumulator `grp`
             const int acc = n_acc == 4 ? (it & 3) : (it & 1);
@@ -451,7 +454,7 @@ void conv_launch(const ConvArgs &a, int grid, cudaStream_t stream) {
         cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
         attr_set = true;
     }
-    conv_umma_kernel<<<grid, kConvThreads, conv_smem_bytes(a), stream>>>(a);
+    launch_pdl(conv_umma_kernel, dim3(grid), dim3(kConvThreads), conv_smem_bytes(a), stream, a);
 }
 
 }  // namespace ry

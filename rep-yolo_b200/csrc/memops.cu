@@ -23,6 +23,8 @@ template <int COUT>
 __global__ void __launch_bounds__(128) stem_kernel(const float *__restrict__ img, const float *__restrict__ w,
                                                    const float *__restrict__ bias, __nv_bfloat16 *__restrict__ out,
                                                    int B, int H, int W, int out_cs, int out_off) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float sw[27 * COUT];
     __shared__ float sb[COUT];
     for (int i = threadIdx.x; i < 27 * COUT; i += blockDim.x) sw[i] = w[i];
@@ -81,6 +83,8 @@ __global__ void __launch_bounds__(kDwThreads) dw5_kernel(const __nv_bfloat16 *__
                                                          const float *__restrict__ w, const float *__restrict__ bias, int C,
                                                          int half, int H, int W, int act, int twp, int th, int tiles_x,
                                                          int tiles_y) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ __align__(16) uint8_t dw_smem[];
     const int hw_ = twp + 4;                                   // halo row length in pixels
     uint4 *tile = reinterpret_cast<uint4 *>(dw_smem);          // [(th+4)][hw_][kDwCv] 16-byte vectors
@@ -156,6 +160,8 @@ __global__ void __launch_bounds__(kDwThreads) dw5_kernel(const __nv_bfloat16 *__
 __global__ void __launch_bounds__(256) maxpool2_kernel(const __nv_bfloat16 *__restrict__ in, int in_cs, int in_off,
                                                        __nv_bfloat16 *__restrict__ out, int out_cs, int out_off, int C,
                                                        int B, int H, int W) {
+    pdl_trigger();
+    pdl_wait();
     const int vecs = C / 8, Ho = H / 2, Wo = W / 2;
     const size_t total = (size_t)B * Ho * Wo * vecs;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -175,6 +181,8 @@ __global__ void __launch_bounds__(256) maxpool2_kernel(const __nv_bfloat16 *__re
 __global__ void __launch_bounds__(256) spp_kernel(const __nv_bfloat16 *__restrict__ in, int in_cs, int in_off,
                                                   __nv_bfloat16 *__restrict__ out, int out_cs, int off5, int off9,
                                                   int off13, int C, int H, int W, int CH) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ __align__(16) uint8_t spp_smem[];
     const int vecs = CH / 8, HW = H * W, n = HW * vecs;
     uint4 *A = reinterpret_cast<uint4 *>(spp_smem), *Bf = A + n;
@@ -219,6 +227,8 @@ __global__ void __launch_bounds__(256) spp_kernel(const __nv_bfloat16 *__restric
 __global__ void __launch_bounds__(256) upsample2_kernel(const __nv_bfloat16 *__restrict__ in, int in_cs, int in_off,
                                                         __nv_bfloat16 *__restrict__ out, int out_cs, int out_off, int C,
                                                         int B, int H, int W) {
+    pdl_trigger();
+    pdl_wait();
     const int vecs = C / 8, Ho = H * 2, Wo = W * 2;
     const size_t total = (size_t)B * Ho * Wo * vecs;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -238,6 +248,8 @@ constexpr int kCaSplits = 16;
 
 __global__ void __launch_bounds__(256) ca_partial_kernel(const __nv_bfloat16 *__restrict__ in, int in_cs, int in_off,
                                                          float *__restrict__ partial, int C, int HW) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ float ca_sm[];         // [256 * 8] partials
     const int b = blockIdx.x / kCaSplits, sp = blockIdx.x % kCaSplits, vecs = C / 8;
     const int groups = blockDim.x / vecs;    // pixel groups working in parallel (C <= 2048)
@@ -267,6 +279,8 @@ __global__ void __launch_bounds__(256) ca_partial_kernel(const __nv_bfloat16 *__
 __global__ void __launch_bounds__(256) ca_finish_kernel(const float *__restrict__ partial, float *__restrict__ out, int out_cs,
                                                         int out_off, const float *__restrict__ f1, const float *__restrict__ f2,
                                                         int C, int HW) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ float ca_sm[];         // [C] mean, [C/16] hidden
     float *mean = ca_sm, *hid = ca_sm + C;
     const int b = blockIdx.x;
@@ -307,10 +321,10 @@ int stem_launch(const float *img, const float *w27, const float *bias, __nv_bflo
     const size_t total = (size_t)B * (H / 2) * (W / 2);
     const int grid = grid_for(total, 128);
     switch (cout) {
-        case 16: stem_kernel<16><<<grid, 128, 0, st>>>(img, w27, bias, out, B, H, W, out_cs, out_off); break;
-        case 32: stem_kernel<32><<<grid, 128, 0, st>>>(img, w27, bias, out, B, H, W, out_cs, out_off); break;
-        case 48: stem_kernel<48><<<grid, 128, 0, st>>>(img, w27, bias, out, B, H, W, out_cs, out_off); break;
-        case 64: stem_kernel<64><<<grid, 128, 0, st>>>(img, w27, bias, out, B, H, W, out_cs, out_off); break;
+        case 16: launch_pdl(stem_kernel<16>, dim3(grid), dim3(128), 0, st, img, w27, bias, out, B, H, W, out_cs, out_off); break;
+        case 32: launch_pdl(stem_kernel<32>, dim3(grid), dim3(128), 0, st, img, w27, bias, out, B, H, W, out_cs, out_off); break;
+        case 48: launch_pdl(stem_kernel<48>, dim3(grid), dim3(128), 0, st, img, w27, bias, out, B, H, W, out_cs, out_off); break;
+        case 64: launch_pdl(stem_kernel<64>, dim3(grid), dim3(128), 0, st, img, w27, bias, out, B, H, W, out_cs, out_off); break;
         default: return 1;
     }
     return 0;
@@ -336,7 +350,7 @@ void dw5_launch(const __nv_bfloat16 *in, int in_cs, int in_off0, int in_off1, __
         cudaFuncSetAttribute(dw5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
         attr_set = true;
     }
-    dw5_kernel<<<B * tiles_y * tiles_x * (C / 32), kDwThreads, smem, st>>>(in, in_cs, in_off0, in_off1, out, out_cs, out_off0, out_off1,
+    launch_pdl(dw5_kernel, dim3(B * tiles_y * tiles_x * (C / 32)), dim3(kDwThreads), smem, st, in, in_cs, in_off0, in_off1, out, out_cs, out_off0, out_off1,
                                                                          w, bias, C, half, H, W, act, best_twp, best_th, tiles_x,
                                                                          tiles_y);
 }
@@ -344,7 +358,7 @@ void dw5_launch(const __nv_bfloat16 *in, int in_cs, int in_off0, int in_off1, __
 void maxpool2_launch(const __nv_bfloat16 *in, int in_cs, int in_off, __nv_bfloat16 *out, int out_cs, int out_off, int C,
                      int B, int H, int W, cudaStream_t st) {
     const size_t total = (size_t)B * (H / 2) * (W / 2) * (C / 8);
-    maxpool2_kernel<<<grid_for(total, 256), 256, 0, st>>>(in, in_cs, in_off, out, out_cs, out_off, C, B, H, W);
+    launch_pdl(maxpool2_kernel, dim3(grid_for(total, 256)), dim3(256), 0, st, in, in_cs, in_off, out, out_cs, out_off, C, B, H, W);
 }
 
 void spp_launch(const __nv_bfloat16 *in, int in_cs, int in_off, __nv_bfloat16 *out, int out_cs, int off5, int off9,
@@ -357,21 +371,21 @@ void spp_launch(const __nv_bfloat16 *in, int in_cs, int in_off, __nv_bfloat16 *o
         cudaFuncSetAttribute(spp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         attr_set = true;
     }
-    spp_kernel<<<B * (C / CH), 256, smem, st>>>(in, in_cs, in_off, out, out_cs, off5, off9, off13, C, H, W, CH);
+    launch_pdl(spp_kernel, dim3(B * (C / CH)), dim3(256), smem, st, in, in_cs, in_off, out, out_cs, off5, off9, off13, C, H, W, CH);
 }
 
 void upsample2_launch(const __nv_bfloat16 *in, int in_cs, int in_off, __nv_bfloat16 *out, int out_cs, int out_off, int C,
                       int B, int H, int W, cudaStream_t st) {
     const size_t total = (size_t)B * (2 * H) * (2 * W) * (C / 8);
-    upsample2_kernel<<<grid_for(total, 256), 256, 0, st>>>(in, in_cs, in_off, out, out_cs, out_off, C, B, H, W);
+    launch_pdl(upsample2_kernel, dim3(grid_for(total, 256)), dim3(256), 0, st, in, in_cs, in_off, out, out_cs, out_off, C, B, H, W);
 }
 
 size_t ca_scratch_bytes(int B, int C) { return (size_t)B * kCaSplits * C * sizeof(float); }
 
 void ca_launch(const __nv_bfloat16 *in, int in_cs, int in_off, float *out, int out_cs, int out_off, const float *f1,
                const float *f2, int C, int B, int HW, float *scratch, cudaStream_t st) {
-    ca_partial_kernel<<<B * kCaSplits, 256, 256 * 8 * sizeof(float), st>>>(in, in_cs, in_off, scratch, C, HW);
-    ca_finish_kernel<<<B, 256, (size_t)(C + C / 16) * sizeof(float), st>>>(scratch, out, out_cs, out_off, f1, f2, C, HW);
+    launch_pdl(ca_partial_kernel, dim3(B * kCaSplits), dim3(256), 256 * 8 * sizeof(float), st, in, in_cs, in_off, scratch, C, HW);
+    launch_pdl(ca_finish_kernel, dim3(B), dim3(256), (size_t)(C + C / 16) * sizeof(float), st, scratch, out, out_cs, out_off, f1, f2, C, HW);
 }
 
 }  // namespace ry
