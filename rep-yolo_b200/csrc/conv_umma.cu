@@ -35,35 +35,45 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+__device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+
 // 8 accumulator columns -> bias, activation, optional residual / per-image vector -> 8 bf16 (one 16-byte chunk).
 //   t = acc*scale + sbias (sbias is pre-multiplied by scale: 0.5 for SiLU, 1 for identity)
 //   SiLU(x) = x*sigmoid(x) = h + h*tanh(h), h = x/2   (one MUFU.TANH instead of EX2 + RCP)
-__device__ __forceinline__ uint4 epi_chunk8(const ConvArgs &p, const uint32_t *raw, const float *sb, float scale, bool valid,
-                                           size_t pix, int img, int ch) {
+// EXTRA = false compiles the residual / broadcast-add paths out (predicated-off instructions still cost issue slots).
+template <bool EXTRA>
+__device__ __forceinline__ uint4 epi_chunk8(const ConvArgs &p, const uint32_t *raw, uint32_t sb_addr, float scale, bool act,
+                                           bool valid, size_t pix, int img, int ch) {
     float x[8];
-    const float4 b0 = *reinterpret_cast<const float4 *>(sb), b1 = *reinterpret_cast<const float4 *>(sb + 4);
+    const float4 b0 = ld_shared_f4(sb_addr), b1 = ld_shared_f4(sb_addr + 16);
     const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
     for (int i = 0; i < 8; ++i) x[i] = fmaf(__uint_as_float(raw[i]), scale, bb[i]);
-    if (p.act == 1) {
+    if (act) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) x[i] = fmaf(x[i], ptx::tanh_approx(x[i]), x[i]);
     }
-    if (p.res != nullptr && valid) {
-        const uint4 r = __ldg(reinterpret_cast<const uint4 *>(p.res + pix * p.res_cs + p.res_off + ch));
-        const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
+    if (EXTRA) {
+        if (p.res != nullptr && valid) {
+            const uint4 r = __ldg(reinterpret_cast<const uint4 *>(p.res + pix * p.res_cs + p.res_off + ch));
+            const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float2 f = unpack_bf16x2(rw[i]);
-            x[2 * i] += f.x;
-            x[2 * i + 1] += f.y;
+            for (int i = 0; i < 4; ++i) {
+                const float2 f = unpack_bf16x2(rw[i]);
+                x[2 * i] += f.x;
+                x[2 * i + 1] += f.y;
+            }
         }
-    }
-    if (p.bvec != nullptr && valid) {
-        const float4 *bv = reinterpret_cast<const float4 *>(p.bvec + (size_t)img * p.bvec_cs + p.bvec_off + ch);
-        const float4 v0 = __ldg(bv), v1 = __ldg(bv + 1);
-        x[0] += v0.x; x[1] += v0.y; x[2] += v0.z; x[3] += v0.w;
-        x[4] += v1.x; x[5] += v1.y; x[6] += v1.z; x[7] += v1.w;
+        if (p.bvec != nullptr && valid) {
+            const float4 *bv = reinterpret_cast<const float4 *>(p.bvec + (size_t)img * p.bvec_cs + p.bvec_off + ch);
+            const float4 v0 = __ldg(bv), v1 = __ldg(bv + 1);
+            x[0] += v0.x; x[1] += v0.y; x[2] += v0.z; x[3] += v0.w;
+            x[4] += v1.x; x[5] += v1.y; x[6] += v1.z; x[7] += v1.w;
+        }
     }
     return make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]), pack_bf16x2(x[6], x[7]));
 }
@@ -203,6 +213,124 @@ __device__ __forceinline__ void mma_role_ks(const ConvArgs &p, const MmaCtx &cx)
     }
 }
 
+
+struct EpiCtx {
+    uint64_t *tfull, *tempty;
+    uint32_t tmem_base, stage_u, sbias_u;
+    uint8_t *sStage;
+    int total_tiles, n_acc, warp, lane;
+};
+
+// Epilogue role (mode 0): 2 groups x 4 warps (TMEM lane quarter = warp % 4).  ep_teams: the groups take alternate tiles,
+// otherwise disjoint column segments of every tile.  TMEM -> registers -> bias/act(/extras) -> bf16 -> swizzled staging ->
+// TMA store (two staging buffers per group; the leader lane tracks the bulk groups).
+template <bool EXTRA>
+__device__ __forceinline__ void epilogue_store_role(const ConvArgs &p, const EpiCtx &cx) {
+    const int e = cx.warp - 2, lane = cx.lane;
+    const int grp = e >> 2;
+    const int quarter = cx.warp & 3;
+    const bool leader = (e & 3) == 0 && lane == 0;
+    const int row = quarter * 32 + lane;
+    const float scale = p.act == 1 ? 0.5f : 1.0f;
+    const bool act = p.act == 1;
+    int w_in = 0, h_in = 0, n_in = 0;
+    if (EXTRA) { w_in = row % p.tw; h_in = (row / p.tw) % p.th; n_in = row / (p.tw * p.th); }
+    const uint32_t stage_u = cx.stage_u + grp * 2 * p.stage_buf_bytes;
+    const int n_acc = cx.n_acc;
+    int bufsel = 0, it = 0;
+    for (int t = blockIdx.x; t < cx.total_tiles; t += gridDim.x, ++it) {
+        if (p.ep_teams && (it & 1) != grp) continue;          // tile teams
+        const int acc = n_acc == 4 ? (it & 3) : (it & 1);
+        const uint32_t aph = (uint32_t)(n_acc == 4 ? (it >> 2) : (it >> 1)) & 1u;
+        const TileCoord tc = tile_coord(p, t);
+        bool valid = false;
+        size_t pix = 0;
+        int img = 0;
+        if (EXTRA) {                                          // pixel coordinates: residual / broadcast add only
+            const int w = tc.w0 + w_in, h = tc.h0 + h_in, n = tc.n0 + n_in;
+            valid = (n_in < p.tn) && (w < p.Wo) && (h < p.Ho) && (n < p.Bo);
+            pix = ((size_t)n * p.Ho + h) * p.Wo + w;
+            img = (int)(pix / p.img_hw);
+        }
+        ptx::mbar_wait(cx.tfull + acc, aph);
+        ptx::tc_fence_after();
+        const uint32_t taddr = cx.tmem_base + acc * p.BN + ((uint32_t)(quarter * 32) << 16);
+        const uint32_t sb_tile = cx.sbias_u + (uint32_t)tc.nc0 * 4;
+        for (int si = 0; si < p.nseg[grp]; ++si) {
+            const ConvSeg sg = p.seg[grp][si];
+            const uint32_t buf = stage_u + bufsel * p.stage_buf_bytes;
+            if (leader) ptx::bulk_wait_read<1>();             // the store that last read this buffer is done
+            ptx::bar_sync(1 + grp, 128);
+            const uint32_t rowoff = (uint32_t)row * (uint32_t)(sg.ncol * 2);
+            const uint32_t swz = (uint32_t)sg.swz;
+            for (int c0 = 0; c0 < sg.ncol; c0 += 16) {
+                uint32_t raw[16];
+                const int col = sg.col0 + c0;
+                if (sg.ncol - c0 >= 16) {
+                    ptx::tmem_ld16_nowait(taddr + col, raw);
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const uint4 o = epi_chunk8<EXTRA>(p, raw + 8 * j, sb_tile + (uint32_t)(col + 8 * j) * 4, scale, act, valid, pix,
+                                                          img, tc.nc0 + col + 8 * j);
+                        uint32_t lin = rowoff + (uint32_t)(c0 * 2 + j * 16);
+                        lin ^= ((lin >> 7) & swz) << 4;
+                        st_shared_v4(buf + lin, o);
+                    }
+                } else {
+                    ptx::tmem_ld8_nowait(taddr + col, raw);
+                    ptx::tmem_ld_wait();
+                    const uint4 o = epi_chunk8<EXTRA>(p, raw, sb_tile + (uint32_t)col * 4, scale, act, valid, pix, img, tc.nc0 + col);
+                    uint32_t lin = rowoff + (uint32_t)(c0 * 2);
+                    lin ^= ((lin >> 7) & swz) << 4;
+                    st_shared_v4(buf + lin, o);
+                }
+            }
+            ptx::fence_proxy_async();
+            ptx::bar_sync(1 + grp, 128);
+            if (leader) {
+                ptx::tma_store_4d(p.omap + sg.map, reinterpret_cast<const void *>(cx.sStage + (size_t)(grp * 2 + bufsel) * p.stage_buf_bytes),
+                                  sg.chan + tc.nc0, tc.w0, tc.h0, tc.n0);
+                ptx::bulk_commit();
+            }
+            bufsel ^= 1;
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(cx.tempty + acc);
+    }
+    if (leader) ptx::bulk_wait_read<0>();                     // staging must outlive the last TMA store's read
+}
+
+// Epilogue role (mode 1): Detect decode, direct fp32 stores.  Group g handles accumulator columns [16g, 16g+16).
+__device__ __forceinline__ void epilogue_detect_role(const ConvArgs &p, const EpiCtx &cx) {
+    const int e = cx.warp - 2, lane = cx.lane;
+    const int grp = e >> 2;
+    const int quarter = cx.warp & 3;
+    const int row = quarter * 32 + lane;
+    const int w_in = row % p.tw, h_in = (row / p.tw) % p.th, n_in = row / (p.tw * p.th);
+    const int n_acc = cx.n_acc;
+    int it = 0;
+    for (int t = blockIdx.x; t < cx.total_tiles; t += gridDim.x, ++it) {
+        const int acc = n_acc == 4 ? (it & 3) : (it & 1);
+        const uint32_t aph = (uint32_t)(n_acc == 4 ? (it >> 2) : (it >> 1)) & 1u;
+        const TileCoord tc = tile_coord(p, t);
+        const int w = tc.w0 + w_in, h = tc.h0 + h_in, n = tc.n0 + n_in;
+        const bool valid = (n_in < p.tn) && (w < p.Wo) && (h < p.Ho) && (n < p.Bo);
+        const size_t pix = ((size_t)n * p.Ho + h) * p.Wo + w;
+        ptx::mbar_wait(cx.tfull + acc, aph);
+        ptx::tc_fence_after();
+        const uint32_t taddr = cx.tmem_base + acc * p.BN + ((uint32_t)(quarter * 32) << 16);
+        uint32_t raw[16];
+        ptx::tmem_ld16_nowait(taddr + grp * 16, raw);
+        ptx::tmem_ld_wait();
+        if (valid && grp * 16 < p.cout) detect_epilogue(p, raw, grp * 16, pix);
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(cx.tempty + acc);
+    }
+}
+
 __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const __grid_constant__ ConvArgs p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -322,85 +450,15 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const __grid
         }
         __syncwarp();
     } else {
-        // ===================== epilogue: 2 column groups x 4 warps (TMEM lane quarter = warp % 4) =====================
-        const int e = warp - 2;
-        const int grp = e >> 2;
-        const int quarter = warp & 3;
-        const bool leader = (e & 3) == 0 && lane == 0;
-        const int row = quarter * 32 + lane;
-        const int w_in = row % p.tw, h_in = (row / p.tw) % p.th, n_in = row / (p.tw * p.th);
-        const float scale = p.act == 1 ? 0.5f : 1.0f;
-        const bool need_pix = p.mode != 0 || p.res != nullptr || p.bvec != nullptr;
-        const uint32_t stage_u = ptx::smem_u32(sStage) + grp * 2 * p.stage_buf_bytes;
-        int bufsel = 0, it = 0;
+        // ===================== epilogue =====================
+        EpiCtx cx;
+        cx.tfull = tfull; cx.tempty = tempty; cx.tmem_base = tmem_base; cx.stage_u = ptx::smem_u32(sStage);
+        cx.sbias_u = ptx::smem_u32(sbias); cx.sStage = sStage; cx.total_tiles = total_tiles; cx.n_acc = n_acc;
+        cx.warp = warp; cx.lane = lane;
         pdl_wait();                 // residual / per-image vector reads and all output writes come after the prerequisites
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
-            if (p.ep_teams && (it & 1) != grp) continue;          // tile teams: this team's tiles use accumulator `grp`
-            const int acc = n_acc == 4 ? (it & 3) : (it & 1);
-            const uint32_t aph = (uint32_t)(n_acc == 4 ? (it >> 2) : (it >> 1)) & 1u;
-            const TileCoord tc = tile_coord(p, t);
-            bool valid = false;
-            size_t pix = 0;
-            int img = 0;
-            if (need_pix) {                                       // pixel coordinates: residual / broadcast add / Detect only
-                const int w = tc.w0 + w_in, h = tc.h0 + h_in, n = tc.n0 + n_in;
-                valid = (n_in < p.tn) && (w < p.Wo) && (h < p.Ho) && (n < p.Bo);
-                pix = ((size_t)n * p.Ho + h) * p.Wo + w;
-                img = (int)(pix / p.img_hw);
-            }
-            ptx::mbar_wait(tfull + acc, aph);
-            ptx::tc_fence_after();
-            const uint32_t taddr = tmem_base + acc * p.BN + ((uint32_t)(quarter * 32) << 16);
-            if (p.mode == 0) {
-                for (int si = 0; si < p.nseg[grp]; ++si) {
-                    const ConvSeg sg = p.seg[grp][si];
-                    const uint32_t buf = stage_u + bufsel * p.stage_buf_bytes;
-                    if (leader) ptx::bulk_wait_read<1>();           // the store that last read this buffer is done
-                    ptx::bar_sync(1 + grp, 128);
-                    const uint32_t rowoff = (uint32_t)row * (uint32_t)(sg.ncol * 2);
-                    for (int c0 = 0; c0 < sg.ncol; c0 += 16) {
-                        uint32_t raw[16];
-                        const int col = sg.col0 + c0;
-                        if (sg.ncol - c0 >= 16) {
-                            ptx::tmem_ld16_nowait(taddr + col, raw);
-                            ptx::tmem_ld_wait();
-#pragma unroll
-                            for (int j = 0; j < 2; ++j) {
-                                const uint4 o = epi_chunk8(p, raw + 8 * j, sbias + tc.nc0 + col + 8 * j, scale, valid, pix, img,
-                                                           tc.nc0 + col + 8 * j);
-                                uint32_t lin = rowoff + (uint32_t)(c0 * 2 + j * 16);
-                                lin ^= ((lin >> 7) & (uint32_t)sg.swz) << 4;
-                                st_shared_v4(buf + lin, o);
-                            }
-                        } else {
-                            ptx::tmem_ld8_nowait(taddr + col, raw);
-                            ptx::tmem_ld_wait();
-                            const uint4 o = epi_chunk8(p, raw, sbias + tc.nc0 + col, scale, valid, pix, img, tc.nc0 + col);
-                            uint32_t lin = rowoff + (uint32_t)(c0 * 2);
-                            lin ^= ((lin >> 7) & (uint32_t)sg.swz) << 4;
-                            st_shared_v4(buf + lin, o);
-                        }
-                    }
-                    ptx::fence_proxy_async();
-                    ptx::bar_sync(1 + grp, 128);
-                    if (leader) {
-                        ptx::tma_store_4d(p.omap + sg.map, reinterpret_cast<const void *>(sStage + (size_t)(grp * 2 + bufsel) * p.stage_buf_bytes),
-                                          sg.chan + tc.nc0, tc.w0, tc.h0, tc.n0);
-                        ptx::bulk_commit();
-                    }
-                    bufsel ^= 1;
-                }
-            } else {
-                uint32_t raw[16];
-                ptx::tmem_ld16_nowait(taddr + grp * 16, raw);
-                ptx::tmem_ld_wait();
-                if (valid && grp * 16 < p.cout) detect_epilogue(p, raw, grp * 16, pix);
-            }
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(tempty + acc);
-        }
-        if (leader) ptx::bulk_wait_read<0>();                       // staging must outlive the last TMA store's read
+        if (p.mode != 0) epilogue_detect_role(p, cx);
+        else if (p.res != nullptr || p.bvec != nullptr) epilogue_store_role<true>(p, cx);
+        else epilogue_store_role<false>(p, cx);
     }
 
     ptx::tc_fence_before();
