@@ -235,11 +235,14 @@ __device__ __forceinline__ void epilogue_store_role(const ConvArgs &p, const Epi
     const bool act = p.act == 1;
     int w_in = 0, h_in = 0, n_in = 0;
     if (EXTRA) { w_in = row % p.tw; h_in = (row / p.tw) % p.th; n_in = row / (p.tw * p.th); }
-    const uint32_t stage_u = cx.stage_u + grp * 2 * p.stage_buf_bytes;
+    const int nbuf = p.n_groups == 4 ? 1 : 2;                 // staging buffers per group
+    const int lst = p.ep_teams ? 0 : grp;                     // segment list: teams share list 0
+    const uint32_t stage_u = cx.stage_u + grp * nbuf * p.stage_buf_bytes;
     const int n_acc = cx.n_acc;
+    const int gmask = p.n_groups - 1;
     int bufsel = 0, it = 0;
     for (int t = blockIdx.x; t < cx.total_tiles; t += gridDim.x, ++it) {
-        if (p.ep_teams && (it & 1) != grp) continue;          // tile teams
+        if (p.ep_teams && (it & gmask) != grp) continue;      // tile teams
         const int acc = n_acc == 4 ? (it & 3) : (it & 1);
         const uint32_t aph = (uint32_t)(n_acc == 4 ? (it >> 2) : (it >> 1)) & 1u;
         const TileCoord tc = tile_coord(p, t);
@@ -256,10 +259,12 @@ __device__ __forceinline__ void epilogue_store_role(const ConvArgs &p, const Epi
         ptx::tc_fence_after();
         const uint32_t taddr = cx.tmem_base + acc * p.BN + ((uint32_t)(quarter * 32) << 16);
         const uint32_t sb_tile = cx.sbias_u + (uint32_t)tc.nc0 * 4;
-        for (int si = 0; si < p.nseg[grp]; ++si) {
-            const ConvSeg sg = p.seg[grp][si];
+        for (int si = 0; si < p.nseg[lst]; ++si) {
+            const ConvSeg sg = p.seg[lst][si];
             const uint32_t buf = stage_u + bufsel * p.stage_buf_bytes;
-            if (leader) ptx::bulk_wait_read<1>();             // the store that last read this buffer is done
+            if (leader) {                                     // the store that last read this buffer is done
+                if (nbuf == 2) ptx::bulk_wait_read<1>(); else ptx::bulk_wait_read<0>();
+            }
             ptx::bar_sync(1 + grp, 128);
             const uint32_t rowoff = (uint32_t)row * (uint32_t)(sg.ncol * 2);
             const uint32_t swz = (uint32_t)sg.swz;
@@ -289,11 +294,11 @@ __device__ __forceinline__ void epilogue_store_role(const ConvArgs &p, const Epi
             ptx::fence_proxy_async();
             ptx::bar_sync(1 + grp, 128);
             if (leader) {
-                ptx::tma_store_4d(p.omap + sg.map, reinterpret_cast<const void *>(cx.sStage + (size_t)(grp * 2 + bufsel) * p.stage_buf_bytes),
+                ptx::tma_store_4d(p.omap + sg.map, reinterpret_cast<const void *>(cx.sStage + (size_t)(grp * nbuf + bufsel) * p.stage_buf_bytes),
                                   sg.chan + tc.nc0, tc.w0, tc.h0, tc.n0);
                 ptx::bulk_commit();
             }
-            bufsel ^= 1;
+            if (nbuf == 2) bufsel ^= 1;
         }
         ptx::tc_fence_before();
         __syncwarp();
@@ -331,14 +336,14 @@ __device__ __forceinline__ void epilogue_detect_role(const ConvArgs &p, const Ep
     }
 }
 
-__global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const __grid_constant__ ConvArgs p) {
+__global__ void __launch_bounds__(kConvMaxThreads, 1) conv_umma_kernel(const __grid_constant__ ConvArgs p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int nb_slots = p.b_resident ? p.kblocks : p.b_stages;
     uint8_t *sA = smem;
     uint8_t *sB = sA + (size_t)p.a_stages * p.a_stage_bytes;
     uint8_t *sStage = sB + (size_t)nb_slots * p.b_stage_bytes;
-    float *sbias = reinterpret_cast<float *>(sStage + 4 * (size_t)p.stage_buf_bytes);
+    float *sbias = reinterpret_cast<float *>(sStage + (size_t)(p.n_groups == 4 ? 4 : 4) * p.stage_buf_bytes);
     uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(sbias) + ((p.cout_pad * 4 + 127) & ~127));
     uint64_t *fullA = bars, *emptyA = fullA + 8, *fullB = emptyA + 8, *emptyB = fullB + 8;
     uint64_t *tfull = emptyB + 8, *tempty = tfull + 4, *bres = tempty + 4;
@@ -360,7 +365,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const __grid
         }
         for (int a = 0; a < 4; ++a) {
             ptx::mbar_init(tfull + a, 1);
-            ptx::mbar_init(tempty + a, p.ep_teams ? 4 : 8);
+            ptx::mbar_init(tempty + a, p.ep_teams ? 4 : 4 * p.n_groups);
         }
         ptx::mbar_init(bres, 1);
         ptx::fence_mbar_init();
@@ -473,7 +478,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const __grid
 
 size_t conv_smem_bytes(const ConvArgs &a) {
     const int nb = a.b_resident ? a.kblocks : a.b_stages;
-    return (size_t)a.a_stages * a.a_stage_bytes + (size_t)nb * a.b_stage_bytes + 4 * (size_t)a.stage_buf_bytes +
+    return (size_t)a.a_stages * a.a_stage_bytes + (size_t)nb * a.b_stage_bytes + 4 * (size_t)a.stage_buf_bytes +   // 2x2 or 4x1 buffers
            ((a.cout_pad * 4 + 127) & ~127) + kBarrierBytes + 1024;
 }
 
@@ -512,7 +517,7 @@ void conv_launch(const ConvArgs &a, int grid, cudaStream_t stream) {
         cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
         attr_set = true;
     }
-    launch_pdl(conv_umma_kernel, dim3(grid), dim3(kConvThreads), conv_smem_bytes(a), stream, a);
+    launch_pdl(conv_umma_kernel, dim3(grid), dim3(64 + 128 * a.n_groups), conv_smem_bytes(a), stream, a);
 }
 
 }  // namespace ry

@@ -26,7 +26,7 @@
 
 namespace ry {
 
-constexpr int kConvThreads = 320;
+constexpr int kConvMaxThreads = 576;   // 2 role warps + up to 4 epilogue groups of 4 warps
 constexpr int kConvMaxTaps = 9;
 constexpr int kConvMaxSegs = 8;      // store segments per epilogue column group
 constexpr int kHaloTw = 8, kHaloTh = 16;
@@ -61,13 +61,14 @@ struct ConvArgs {
     int a_stage_bytes, a_stages, a_box_bytes;
     int b_stage_bytes, b_stages, b_resident;
     int n_acc;                 // TMEM accumulator stages: 2 or 4 (4 * BN <= 512)
-    int stage_buf_bytes;       // epilogue staging: 2 groups x 2 buffers of this size
+    int stage_buf_bytes;       // epilogue staging: n_groups x (2 buffers, or 1 when n_groups == 4) of this size
     int mode;                  // 0 = bf16 NHWC store, 1 = Detect decode
-    int ep_teams;              // 1: the two 4-warp epilogue groups take alternate TILES (small N); 0: disjoint COLUMNS of each tile
+    int ep_teams;              // 1: the 4-warp epilogue groups take alternate TILES (small N); 0: disjoint COLUMNS of each tile
+    int n_groups;              // epilogue groups: 2, or 4 (tile teams of the memory-bound small-N layers)
     const float *bias;         // [Cout_pad]
     int cout, cout_pad;
     int act;
-    int nseg[2];
+    int nseg[2];               // tile teams share list 0
     ConvSeg seg[2][kConvMaxSegs];
     const __nv_bfloat16 *res;  // optional residual (same pixel grid), added after the activation
     int res_cs, res_off;

@@ -326,6 +326,7 @@ int bind_conv(ry_plan *p, Op &op, std::vector<CUtensorMap> &maps) {
         a.det_stride = d.fparam[0];
         for (int i = 0; i < 6; ++i) a.anchors[i] = d.fparam[1 + i];
         if (cp.BN != 32) RY_FAIL("detect: na*(nc+5) must be in (16, 32] for the fused decode epilogue");
+        a.n_groups = 2;
         if (conv_plan_smem(a, 8)) RY_FAIL("detect: shared memory plan failed");
         return 0;
     }
@@ -355,6 +356,12 @@ int bind_conv(ry_plan *p, Op &op, std::vector<CUtensorMap> &maps) {
         if (conv_plan_smem(a, *std::max_element(widths, widths + n_widths))) RY_FAIL("conv: shared memory plan failed");
     }
     if (a.nseg[0] > kConvMaxSegs || a.nseg[1] > kConvMaxSegs) RY_FAIL("conv: too many store segments");
+    {
+        static const char *g_env = getenv("RY_CONV_GROUPS");
+        a.n_groups = (a.ep_teams && 4 * cp.BN <= 512) ? 4 : 2;
+        if (g_env && atoi(g_env) == 2) a.n_groups = 2;
+        if (a.n_groups == 4) a.n_acc = 4;
+    }
     for (int wi = 0; wi < n_widths; ++wi) {
         const cuuint64_t oc = (cuuint64_t)tout.d.channels;
         if (k == 1) {
