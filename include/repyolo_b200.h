@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define RY_ABI_VERSION 1
+#define RY_ABI_VERSION 2
 
 typedef struct ry_plan ry_plan;
 
@@ -80,6 +80,8 @@ typedef struct ry_op_desc {
     ry_view in0;           /* main input                                                           */
     ry_view in1;           /* CONV: residual added after act (same shape as out) | attention: q    */
     ry_view in2;           /* CONV: per-image broadcast vector added after act   | attention: k    */
+                           /* CONV with n_src > 1 (1x1 only): in0..in{n_src-1} are the channel-concatenated inputs    */
+                           /* (the torch.cat feeding DER_Block.cv1, common.py:3653, never materialises)               */
     ry_view out0;          /* main output (SPP: the 5x5 pool; ATTN_QK: q)                          */
     ry_view out1;          /* CONV/DW5 split store: second half of the channels | SPP: 9x9 | ATTN_QK: k */
     ry_view out2;          /* SPP: 13x13                                                           */
@@ -88,6 +90,8 @@ typedef struct ry_op_desc {
     int32_t act;           /* ry_act */
     int32_t cin, cout;
     int32_t level_idx;     /* DETECT: pyramid level (row offset / stride / anchors) */
+    int32_t n_src;         /* CONV: number of concatenated input views (0 or 1 = just in0) */
+    int32_t pad_;
     int64_t w_off;         /* byte offsets into the host weight blob; -1 = none.                                    */
     int64_t b_off;         /*   CONV/STEM/DETECT: w = fp32 [cout][cin][k][k] (PyTorch OIHW), b = fp32 [cout]        */
     int64_t aux_off[6];    /*   DW5: w = fp32 [C][5][5]; CA: w = f1 [C/16][C], aux0 = f2 [C][C/16];                 */

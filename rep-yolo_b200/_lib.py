@@ -28,7 +28,7 @@ class OpDesc(C.Structure):
     _fields_ = [('kind', C.c_int32), ('layer', C.c_int32),
                 ('in0', View), ('in1', View), ('in2', View), ('out0', View), ('out1', View), ('out2', View),
                 ('ksize', C.c_int32), ('stride', C.c_int32), ('act', C.c_int32), ('cin', C.c_int32), ('cout', C.c_int32),
-                ('level_idx', C.c_int32), ('w_off', C.c_int64), ('b_off', C.c_int64), ('aux_off', C.c_int64 * 6),
+                ('level_idx', C.c_int32), ('n_src', C.c_int32), ('pad_', C.c_int32), ('w_off', C.c_int64), ('b_off', C.c_int64), ('aux_off', C.c_int64 * 6),
                 ('fparam', C.c_float * 8)]
 
 
@@ -72,7 +72,7 @@ def lib():
     for name in EXPORTS:
         if name not in ('ry_last_error', 'ry_plan_destroy', 'ry_abi_version', 'ry_abi_sizeof'):
             getattr(L, name).restype = i32
-    if L.ry_abi_version() != 1:
+    if L.ry_abi_version() != 2:
         raise NativeError('ABI version mismatch between _lib.py and librepyolo_b200.so')
     L.ry_abi_sizeof.argtypes = [i32]
     L.ry_abi_sizeof.restype = i32

@@ -148,7 +148,7 @@ __device__ __forceinline__ void mma_role(const ConvArgs &p, const MmaCtx &cx) {
         uint32_t accumulate = 0;
         int c = 0;
         for (int ia = 0; ia < n_a; ++ia) {
-            const int ks = KS ? KS : ((c == p.cblk - 1) ? p.ksteps_last : ksteps_full);
+            const int ks = KS ? KS : (p.n_src > 1 ? (int)p.kb_ks[ia] : ((c == p.cblk - 1) ? p.ksteps_last : ksteps_full));
             ptx::mbar_wait(cx.fullA + sa, pha);
             ptx::tc_fence_after();
             const uint64_t a_desc = a_desc0 + (uint64_t)(sa * a_inc);
@@ -204,7 +204,8 @@ __device__ __forceinline__ void mma_role(const ConvArgs &p, const MmaCtx &cx) {
 
 template <bool HALO, bool STREAM_B>
 __device__ __forceinline__ void mma_role_ks(const ConvArgs &p, const MmaCtx &cx) {
-    const int ks = p.cblk == 1 ? p.ksteps_last : (p.ksteps_last == p.kb / 16 ? p.kb / 16 : 0);   // uniform K steps?
+    int ks = p.cblk == 1 ? p.ksteps_last : (p.ksteps_last == p.kb / 16 ? p.kb / 16 : 0);   // uniform K steps?
+    if (p.n_src > 1) ks = 0;
     switch (ks) {
         case 2: mma_role<HALO, STREAM_B, 2>(p, cx); break;
         case 3: mma_role<HALO, STREAM_B, 3>(p, cx); break;
@@ -426,8 +427,12 @@ __global__ void __launch_bounds__(kConvMaxThreads, 1) conv_umma_kernel(const __g
                     ptx::mbar_wait(emptyA + sa, pha ^ 1);
                     if (issuer) {
                         ptx::mbar_expect_tx(fullA + sa, (uint32_t)p.a_box_bytes);
-                        ptx::tma_load_4d(sA + (size_t)sa * p.a_stage_bytes, p.amap + p.tap_map[tap], fullA + sa, cb * p.kb,
-                                         tc.w0 + p.tap_dw[tap], tc.h0 + p.tap_dh[tap], tc.n0);
+                        if (p.n_src > 1)
+                            ptx::tma_load_4d(sA + (size_t)sa * p.a_stage_bytes, p.amap + p.kb_map[kbi], fullA + sa, p.kb_coord[kbi], tc.w0,
+                                             tc.h0, tc.n0);
+                        else
+                            ptx::tma_load_4d(sA + (size_t)sa * p.a_stage_bytes, p.amap + p.tap_map[tap], fullA + sa, cb * p.kb,
+                                             tc.w0 + p.tap_dw[tap], tc.h0 + p.tap_dh[tap], tc.n0);
                     }
                     if (++sa == p.a_stages) { sa = 0; pha ^= 1; }
                     if (stream_b) {

@@ -28,6 +28,7 @@ namespace ry {
 
 constexpr int kConvMaxThreads = 576;   // 2 role warps + up to 4 epilogue groups of 4 warps
 constexpr int kConvMaxTaps = 9;
+constexpr int kConvMaxSrcBlocks = 24;  // K blocks of a multi-source 1x1 conv
 constexpr int kConvMaxSegs = 8;      // store segments per epilogue column group
 constexpr int kHaloTw = 8, kHaloTh = 16;
 
@@ -51,6 +52,9 @@ struct ConvArgs {
     int kblocks;               // ntaps * cblk
     int ksteps_last;           // K=16 MMA steps holding real channels in the last K block of a tap
     int8_t tap_map[kConvMaxTaps], tap_dh[kConvMaxTaps], tap_dw[kConvMaxTaps];
+    int n_src;                 // > 1: 1x1 conv over concatenated inputs; K block i comes from map kb_map[i], channel kb_coord[i]
+    int8_t kb_map[kConvMaxSrcBlocks], kb_ks[kConvMaxSrcBlocks];
+    int16_t kb_coord[kConvMaxSrcBlocks];
     int tw, th, tn;            // output tile extent in w, h, image
     int tiles_w, tiles_h, tiles_n;
     uint32_t div_nt, div_tw, div_th;   // ceil(2^32 / d) for d = n_ntiles, tiles_w, tiles_h (0 when d == 1): exact q = umulhi(n, m)

@@ -54,6 +54,7 @@ struct Tensor {
 struct ConvPacked {          // shape-independent part of a CONV / DETECT op
     int kb = 0, cblk = 0, ksteps_last = 0, ntaps = 0, BN = 0, n_ntiles = 0, k_pad = 0, cout_pad = 0;
     size_t w_dev = 0, b_dev = 0;   // byte offsets in the device weight buffer
+    int n_src = 1, src_len[3] = {0, 0, 0};   // multi-source 1x1: each source padded to whole K blocks
 };
 
 struct Op {
@@ -113,6 +114,18 @@ int pack_conv(const ry_op_desc &d, const unsigned char *host, size_t host_bytes,
     cp.kb = cin > 32 ? 64 : (cin > 16 ? 32 : 16);
     cp.cblk = (cin + cp.kb - 1) / cp.kb;
     cp.ksteps_last = (cin - (cp.cblk - 1) * cp.kb + 15) / 16;
+    cp.n_src = d.n_src > 1 ? d.n_src : 1;
+    if (cp.n_src > 1) {
+        if (k != 1 || cp.n_src > 3) RY_FAIL("conv: concatenated inputs need a 1x1 conv with at most 3 sources");
+        const ry_view *vs[3] = {&d.in0, &d.in1, &d.in2};
+        int tot = 0, maxlen = 0;
+        cp.cblk = 0;
+        for (int i = 0; i < cp.n_src; ++i) { cp.src_len[i] = vs[i]->c_len; tot += vs[i]->c_len; maxlen = std::max(maxlen, vs[i]->c_len); }
+        if (tot != cin) RY_FAIL("conv: concatenated input views do not add up to cin");
+        cp.kb = maxlen > 32 ? 64 : (maxlen > 16 ? 32 : 16);
+        for (int i = 0; i < cp.n_src; ++i) cp.cblk += (cp.src_len[i] + cp.kb - 1) / cp.kb;
+        if (cp.cblk > kConvMaxSrcBlocks) RY_FAIL("conv: too many K blocks for a multi-source conv");
+    }
     cp.ntaps = k * k;
     cp.k_pad = cp.ntaps * cp.cblk * cp.kb;
     const int c16 = (cout + 15) / 16 * 16;
@@ -123,10 +136,20 @@ int pack_conv(const ry_op_desc &d, const unsigned char *host, size_t host_bytes,
     const float *w = reinterpret_cast<const float *>(host + d.w_off);
     const float *b = reinterpret_cast<const float *>(host + d.b_off);
     std::vector<__nv_bfloat16> wp((size_t)cp.cout_pad * cp.k_pad, __float2bfloat16(0.0f));
+    std::vector<int> kcol(cin);                       // packed K column of input channel ci (within a tap)
+    if (cp.n_src > 1) {
+        int ci = 0, blk = 0;
+        for (int s = 0; s < cp.n_src; ++s) {
+            for (int c = 0; c < cp.src_len[s]; ++c) kcol[ci++] = blk * cp.kb + c;
+            blk += (cp.src_len[s] + cp.kb - 1) / cp.kb;
+        }
+    } else {
+        for (int ci = 0; ci < cin; ++ci) kcol[ci] = ci;
+    }
     for (int co = 0; co < cout; ++co)
         for (int ci = 0; ci < cin; ++ci)
             for (int t = 0; t < cp.ntaps; ++t)
-                wp[(size_t)co * cp.k_pad + (size_t)t * cp.cblk * cp.kb + ci] =
+                wp[(size_t)co * cp.k_pad + (size_t)t * cp.cblk * cp.kb + kcol[ci]] =
                     __float2bfloat16_rn(w[((size_t)co * cin + ci) * cp.ntaps + t]);
     std::vector<float> bp(cp.cout_pad, 0.0f);
     for (int co = 0; co < cout; ++co) bp[co] = b[co];
@@ -155,14 +178,15 @@ void pick_tile(int B, int Ho, int Wo, int *tw, int *th, int *tn) {
 }
 
 int encode_map(CUtensorMap *m, void *base, int rank, const cuuint64_t *dims, const cuuint64_t *strides_bytes,
-               const cuuint32_t *box, int kb) {   // kb = inner box extent in bf16 elements: 64/32/16 -> 128/64/32-byte swizzle, 8 -> none
+               const cuuint32_t *box, int kb, bool dense = true) {   // kb = inner box extent in bf16 elements: 64/32/16 -> 128/64/32-byte swizzle, 8 -> none
     EncodeTiledFn enc = get_encode();
     if (!enc) RY_FAIL("cuTensorMapEncodeTiled entry point not available (driver too old?)");
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     const CUtensorMapSwizzle sw = kb == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
                                   : (kb == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : (kb == 16 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE));
     const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, base, dims, strides_bytes, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                           dense ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_NONE,   // channel-slice views: no over-fetch
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) RY_FAIL("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
     return 0;
@@ -243,6 +267,7 @@ int bind_conv(ry_plan *p, Op &op, std::vector<CUtensorMap> &maps) {
     const size_t esz = 2;
     const cuuint64_t ctot = (cuuint64_t)tin.d.channels;
     __nv_bfloat16 *in_base = bf(p, d.in0.tensor) + d.in0.c_off;
+    const bool in_dense = d.in0.c_len == tin.d.channels;
     static const bool no_halo = getenv("RY_CONV_NO_HALO") != nullptr;
     CUtensorMap m;
     a.a_mode = A_BOX;
@@ -251,11 +276,27 @@ int bind_conv(ry_plan *p, Op &op, std::vector<CUtensorMap> &maps) {
         const cuuint64_t P = (cuuint64_t)B * Hi * Wi;
         a.tw = 128; a.th = 1; a.tn = 1;
         a.Wo = (int)P; a.Ho = 1; a.Bo = 1;
-        const cuuint64_t dims[4] = {(cuuint64_t)d.cin, P, 1, 1};
-        const cuuint64_t str[3] = {ctot * esz, P * ctot * esz, P * ctot * esz};
         const cuuint32_t box[4] = {(cuuint32_t)cp.kb, 128, 1, 1};
-        if (encode_map(&m, in_base, 4, dims, str, box, cp.kb)) return 1;
-        maps.push_back(m);
+        a.n_src = cp.n_src;
+        const ry_view *vs[3] = {&d.in0, &d.in1, &d.in2};
+        int blk = 0;
+        for (int si = 0; si < cp.n_src; ++si) {
+            const Tensor &ts = p->tensors[vs[si]->tensor];
+            if (ts.h != Hi || ts.w != Wi) RY_FAIL("conv: concatenated inputs must share one pixel grid");
+            const cuuint64_t cs = (cuuint64_t)ts.d.channels;
+            const cuuint64_t dims[4] = {(cuuint64_t)(cp.n_src > 1 ? vs[si]->c_len : d.cin), P, 1, 1};
+            const cuuint64_t str[3] = {cs * esz, P * cs * esz, P * cs * esz};
+            if (encode_map(&m, bf(p, vs[si]->tensor) + vs[si]->c_off, 4, dims, str, box, cp.kb, vs[si]->c_len == ts.d.channels)) return 1;
+            maps.push_back(m);
+            if (cp.n_src > 1) {
+                const int nb = (cp.src_len[si] + cp.kb - 1) / cp.kb;
+                for (int j = 0; j < nb; ++j, ++blk) {
+                    a.kb_map[blk] = (int8_t)si;
+                    a.kb_coord[blk] = (int16_t)(j * cp.kb);
+                    a.kb_ks[blk] = (int8_t)((std::min(cp.kb, cp.src_len[si] - j * cp.kb) + 15) / 16);
+                }
+            }
+        }
         a.tap_map[0] = 0; a.tap_dh[0] = 0; a.tap_dw[0] = 0;
     } else if (s == 1 && !no_halo && Wo % kHaloTw == 0 && Ho % kHaloTh == 0) {
         // halo mode: one (8+2) x (16+2) pixel box per K block, the nine taps are descriptor windows into it
@@ -266,7 +307,7 @@ int bind_conv(ry_plan *p, Op &op, std::vector<CUtensorMap> &maps) {
         const cuuint64_t dims[4] = {(cuuint64_t)d.cin, (cuuint64_t)Wi, (cuuint64_t)Hi, (cuuint64_t)B};
         const cuuint64_t str[3] = {ctot * esz, (cuuint64_t)Wi * ctot * esz, (cuuint64_t)Hi * Wi * ctot * esz};
         const cuuint32_t box[4] = {(cuuint32_t)cp.kb, (cuuint32_t)(kHaloTw + 2), (cuuint32_t)(kHaloTh + 2), 1};
-        if (encode_map(&m, in_base, 4, dims, str, box, cp.kb)) return 1;
+        if (encode_map(&m, in_base, 4, dims, str, box, cp.kb, in_dense)) return 1;
         maps.push_back(m);
     } else {
         pick_tile(B, Ho, Wo, &a.tw, &a.th, &a.tn);
@@ -275,7 +316,7 @@ int bind_conv(ry_plan *p, Op &op, std::vector<CUtensorMap> &maps) {
         if (s == 1) {
             const cuuint64_t dims[4] = {(cuuint64_t)d.cin, (cuuint64_t)Wi, (cuuint64_t)Hi, (cuuint64_t)B};
             const cuuint64_t str[3] = {ctot * esz, (cuuint64_t)Wi * ctot * esz, (cuuint64_t)Hi * Wi * ctot * esz};
-            if (encode_map(&m, in_base, 4, dims, str, box, cp.kb)) return 1;
+            if (encode_map(&m, in_base, 4, dims, str, box, cp.kb, in_dense)) return 1;
             maps.push_back(m);
             for (int t = 0; t < 9; ++t) { a.tap_map[t] = 0; a.tap_dh[t] = (int8_t)(t / 3 - 1); a.tap_dw[t] = (int8_t)(t % 3 - 1); }
         } else {
@@ -285,7 +326,7 @@ int bind_conv(ry_plan *p, Op &op, std::vector<CUtensorMap> &maps) {
                     const cuuint64_t dims[4] = {(cuuint64_t)d.cin, (cuuint64_t)((Wi - pw + 1) / 2), (cuuint64_t)((Hi - ph + 1) / 2),
                                                 (cuuint64_t)B};
                     const cuuint64_t str[3] = {2 * ctot * esz, 2 * (cuuint64_t)Wi * ctot * esz, (cuuint64_t)Hi * Wi * ctot * esz};
-                    if (encode_map(&m, in_base + ((size_t)ph * Wi + pw) * ctot, 4, dims, str, box, cp.kb)) return 1;
+                    if (encode_map(&m, in_base + ((size_t)ph * Wi + pw) * ctot, 4, dims, str, box, cp.kb, false)) return 1;
                     maps.push_back(m);
                 }
             for (int t = 0; t < 9; ++t) {
@@ -378,12 +419,12 @@ int bind_conv(ry_plan *p, Op &op, std::vector<CUtensorMap> &maps) {
         }
         maps.push_back(m);
     }
-    if (d.in1.tensor >= 0) {
+    if (cp.n_src <= 1 && d.in1.tensor >= 0) {
         a.res = bf(p, d.in1.tensor);
         a.res_cs = p->tensors[d.in1.tensor].d.channels;
         a.res_off = d.in1.c_off;
     }
-    if (d.in2.tensor >= 0) {
+    if (cp.n_src <= 1 && d.in2.tensor >= 0) {
         a.bvec = f32(p, d.in2.tensor);
         a.bvec_cs = p->tensors[d.in2.tensor].d.channels;
         a.bvec_off = d.in2.c_off;

@@ -75,6 +75,7 @@ class Plan:
             setattr(d, name, N.View(t, o, n))
         d.ksize, d.stride, d.act = kw.get('ksize', 1), kw.get('stride', 1), kw.get('act', N.ACT_NONE)
         d.cin, d.cout, d.level_idx = kw.get('cin', 0), kw.get('cout', 0), kw.get('level_idx', 0)
+        d.n_src = kw.get('n_src', 1)
         d.w_off, d.b_off = kw.get('w_off', -1), kw.get('b_off', -1)
         aux = kw.get('aux', [])
         for i in range(6):
@@ -87,6 +88,12 @@ class Plan:
 
     def conv(self, layer, w, b, src, dst, stride=1, act=True, dst2=None, res=None, bvec=None):
         cout, cin, k, _ = w.shape
+        if isinstance(src, list):            # 1x1 conv over the channel concatenation of several views (no copy)
+            assert k == 1 and res is None and bvec is None and 1 < len(src) <= 3 and sum(v[2] for v in src) == cin
+            views = src + [None] * (3 - len(src))
+            return self.op(N.OP_CONV, layer, in0=views[0], in1=views[1], in2=views[2], out0=dst, out1=dst2, ksize=1, stride=1,
+                           act=N.ACT_SILU if act else N.ACT_NONE, cin=cin, cout=cout, n_src=len(src), w_off=self.blob.add(w),
+                           b_off=self.blob.add(b))
         assert src[2] == cin, (layer, src, w.shape)
         assert (dst[2] + (dst2[2] if dst2 else 0)) == cout, (layer, dst, dst2, w.shape)
         return self.op(N.OP_CONV, layer, in0=src, in1=res, in2=bvec, out0=dst, out1=dst2, ksize=k, stride=stride,
@@ -182,10 +189,11 @@ def lower(layers, fz, nc=1):
             lvl = 1
         elif L.kind == 'DER_Block':                                  # common.py:3644-3654
             c1, lvl = a[0], lvl_in
-            cat = P.tensor(3 * c1, lvl)
+            # x1 / x4_1 / x4_3 stay separate dense tensors: cv1 reads its three inputs through three TMA maps, so neither the
+            # concat nor channel-slice (96-byte runs at a 288-byte pitch) traffic exists
+            x1, x41, x43 = (P.full(P.tensor(c1, lvl)) for _ in range(3))
             x2, x3, x42 = (P.full(P.tensor(c1, lvl)) for _ in range(3))
             h1, h2 = P.full(P.tensor(c1 // 2, lvl)), P.full(P.tensor(c1 // 2, lvl))
-            x1, x41, x43 = (cat, 0, c1), (cat, c1, c1), (cat, 2 * c1, c1)
             P.conv(L.i, *W(f'{p}.stage1.0.reparam_conv'), x, x1)
             P.conv(L.i, *W(f'{p}.stage2.0.reparam_conv'), x1, x2)
             P.conv(L.i, *W(f'{p}.stage3.0.reparam_conv'), x2, x3)
@@ -194,7 +202,7 @@ def lower(layers, fz, nc=1):
                 P.conv(L.i, *W(f'{p}.stage{stage}.0.reparam_conv'), h1, h2)
                 P.conv(L.i, *W(f'{p}.cv{j}_2.conv'), h2, dstv)
             dst = out_view(L, lvl)
-            P.conv(L.i, *W(f'{p}.cv1.conv'), P.full(cat), dst)
+            P.conv(L.i, *W(f'{p}.cv1.conv'), [x1, x41, x43], dst)
         elif L.kind == 'MP':
             lvl = lvl_in + 1
             dst = out_view(L, lvl)
