@@ -16,55 +16,150 @@ __device__ __forceinline__ uint4 ldg16(const __nv_bfloat16 *p) { return __ldg(re
 __device__ __forceinline__ void stg16(__nv_bfloat16 *p, uint4 v) { *reinterpret_cast<uint4 *>(p) = v; }
 
 // ------------------------------------------------------------------------------------------------------------------
-// Stem: RepS_Block L0 deploy branch (reference models/common.py:3412-3416): SiLU(conv3x3 s2 p1 (x) + b), Cin = 3.
-// One thread = one output pixel, all COUT channels in registers; weights [27][COUT] fp32 in shared memory.
+// Stem: RepS_Block L0 deploy branch (reference models/common.py:3412-3416): SiLU(conv3x3 s2 p1 (x) + b), Cin = 3, on the
+// fp32 NCHW image -> NHWC bf16.  K = 27 (padded to 32) is far too small for a tcgen05 tile pipeline but 1296 FMA per
+// pixel would make a SIMT kernel FMA-bound at ~1.6x the HBM floor, so the product runs on mma.sync m16n8k16 (bf16 in,
+// fp32 accumulate): one CTA tile = 2 output rows x 64 output pixels; the 5 x 130 x 3 input patch is staged in shared
+// memory as bf16, each warp gathers the im2col A fragments of its 16 pixels with 16-bit shared loads, the weight B
+// fragments live in registers for the whole kernel; bias + SiLU; the tile goes out through shared memory as coalesced
+// 16-byte stores.
 // ------------------------------------------------------------------------------------------------------------------
+constexpr int kStemTW = 64, kStemTH = 8, kStemPW = 2 * kStemTW + 2, kStemPitch = 136;   // patch row: 130 used of 136
+// one CTA tile = 8 output rows x 64 pixels: the 17-row input patch is fetched once (26 independent loads per thread),
+// then four row pairs are computed, staged and stored
+
+__device__ __forceinline__ void mma_bf16_16816(float *c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+constexpr int kStemLines = 3 * (2 * kStemTH + 1);                       // (channel, input row) lines of one patch
+constexpr int kStemPatchFloats = kStemLines * kStemPitch;
+
+__device__ __forceinline__ void cp_async4(uint32_t dst, const float *src, bool ok) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(ok ? 4 : 0) : "memory");   // !ok: zero fill
+}
+
 template <int COUT>
-__global__ void __launch_bounds__(128) stem_kernel(const float *__restrict__ img, const float *__restrict__ w,
+__global__ void __launch_bounds__(256) stem_kernel(const float *__restrict__ img, const float *__restrict__ w,
                                                    const float *__restrict__ bias, __nv_bfloat16 *__restrict__ out,
                                                    int B, int H, int W, int out_cs, int out_off) {
     pdl_trigger();
-    pdl_wait();
-    __shared__ float sw[27 * COUT];
-    __shared__ float sb[COUT];
-    for (int i = threadIdx.x; i < 27 * COUT; i += blockDim.x) sw[i] = w[i];
-    for (int i = threadIdx.x; i < COUT; i += blockDim.x) sb[i] = bias[i];
-    __syncthreads();
+    constexpr int NT = COUT / 8;
+    extern __shared__ __align__(16) uint8_t stem_smem[];
+    float *patch = reinterpret_cast<float *>(stem_smem);                       // 2 x [lines][pitch] fp32, filled by cp.async
+    __nv_bfloat16 *stage = reinterpret_cast<__nv_bfloat16 *>(patch + 2 * kStemPatchFloats);   // [2 rows][64 px][COUT]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
     const int Ho = H / 2, Wo = W / 2;
-    const size_t total = (size_t)B * Ho * Wo;
-    for (size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x; pix < total; pix += (size_t)gridDim.x * blockDim.x) {
-        const int wo = (int)(pix % Wo);
-        const int ho = (int)((pix / Wo) % Ho);
-        const int b = (int)(pix / ((size_t)Wo * Ho));
-        float acc[COUT];
+    // ---- per-thread constants: patch offsets of this thread's 8 K indices, weight fragments, bias ----
+    int koff[8];
+    bool kval[8];
 #pragma unroll
-        for (int c = 0; c < COUT; ++c) acc[c] = sb[c];
-        const float *ib = img + (size_t)b * 3 * H * W;
+    for (int s = 0; s < 2; ++s)
 #pragma unroll
-        for (int ci = 0; ci < 3; ++ci) {
+        for (int j = 0; j < 4; ++j) {
+            const int k = s * 16 + 2 * t4 + (j & 1) + (j >> 1) * 8;
+            kval[s * 4 + j] = k < 27;
+            const int ci = k / 9, kh = (k % 9) / 3, kw = k % 3;
+            koff[s * 4 + j] = k < 27 ? (ci * (2 * kStemTH + 1) + kh) * kStemPitch + kw : 0;
+        }
+    uint32_t bw[NT][2][2];
 #pragma unroll
-            for (int kh = 0; kh < 3; ++kh) {
-                const int hi = 2 * ho + kh - 1;
+    for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-                for (int kw = 0; kw < 3; ++kw) {
-                    const int wi = 2 * wo + kw - 1;
-                    float x = 0.0f;
-                    if (hi >= 0 && hi < H && wi >= 0 && wi < W) x = __ldg(ib + ((size_t)ci * H + hi) * W + wi);
-                    const float *wr = sw + ((ci * 3 + kh) * 3 + kw) * COUT;
+        for (int s = 0; s < 2; ++s)
 #pragma unroll
-                    for (int c = 0; c < COUT; ++c) acc[c] = fmaf(x, wr[c], acc[c]);
-                }
+            for (int h = 0; h < 2; ++h) {
+                const int k0 = s * 16 + 2 * t4 + h * 8, n = nt * 8 + g;
+                const float w0 = k0 < 27 ? __ldg(w + k0 * COUT + n) : 0.0f, w1 = k0 + 1 < 27 ? __ldg(w + (k0 + 1) * COUT + n) : 0.0f;
+                bw[nt][s][h] = pack_bf16x2(w0, w1);
+            }
+    float bb[NT][2];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) { bb[nt][0] = __ldg(bias + nt * 8 + 2 * t4); bb[nt][1] = __ldg(bias + nt * 8 + 2 * t4 + 1); }
+    pdl_wait();
+    const int tiles_x = cdiv(Wo, kStemTW), tiles_y = cdiv(Ho, kStemTH);
+    const int total = B * tiles_y * tiles_x;
+    const uint32_t patch_u = (uint32_t)__cvta_generic_to_shared(patch);
+
+    auto prefetch = [&](int tile, int buf) {       // asynchronous fill of one patch buffer (zero fill outside the image)
+        const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
+        const int hi0 = 2 * ty * kStemTH - 1, wi0 = 2 * tx * kStemTW - 1;
+        for (int r = warp; r < kStemLines; r += 8) {   // one warp per (channel, input row) line
+            const int ci = r / (2 * kStemTH + 1), yy = hi0 + r - ci * (2 * kStemTH + 1);
+            const bool row_ok = yy >= 0 && yy < H;
+            const float *src = img + (((size_t)b * 3 + ci) * H + (row_ok ? yy : 0)) * W;
+            const uint32_t dst = patch_u + (uint32_t)(buf * kStemPatchFloats + r * kStemPitch) * 4;
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+                const int x = lane + 32 * j, xx = wi0 + x;
+                const bool ok = row_ok && xx >= 0 && xx < W;
+                if (x < kStemPW) cp_async4(dst + x * 4, src + (ok ? xx : 0), ok);
             }
         }
-        __nv_bfloat16 *o = out + pix * out_cs + out_off;
-#pragma unroll
-        for (int c = 0; c < COUT; c += 8) {
-            float s[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) s[i] = silu_f(acc[c + i]);
-            stg16(o + c, make_uint4(pack_bf16x2(s[0], s[1]), pack_bf16x2(s[2], s[3]), pack_bf16x2(s[4], s[5]),
-                                    pack_bf16x2(s[6], s[7])));
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    int buf = 0;
+    if (blockIdx.x < total) prefetch(blockIdx.x, 0);
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, buf ^= 1) {
+        const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
+        const int wo0 = tx * kStemTW, ho0 = ty * kStemTH;
+        const int next = tile + gridDim.x;
+        if (next < total) {
+            prefetch(next, buf ^ 1);                      // overlaps this tile's compute
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
+        __syncthreads();
+        const float *pb = patch + buf * kStemPatchFloats;
+        for (int rp = 0; rp < kStemTH / 2; ++rp) {
+            // ---- warp = 16 consecutive pixels of one row of this row pair ----
+            const int trow = warp / 4, px0 = (warp % 4) * 16;
+            const float *pp = pb + (2 * (2 * rp + trow)) * kStemPitch + 2 * px0;
+            uint32_t a[2][4];
+#pragma unroll
+            for (int s = 0; s < 2; ++s)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {               // h: k pair (2t,2t+1) / (2t+8,2t+9)
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {           // r: pixel g / g+8
+                        const int pix = 2 * (g + 8 * r);
+                        const float lo = kval[s * 4 + 2 * h] ? pp[koff[s * 4 + 2 * h] + pix] : 0.0f;
+                        const float hi = kval[s * 4 + 2 * h + 1] ? pp[koff[s * 4 + 2 * h + 1] + pix] : 0.0f;
+                        a[s][h * 2 + r] = pack_bf16x2(lo, hi);   // a0:(g,k lo) a1:(g+8,k lo) a2:(g,k hi) a3:(g+8,k hi)
+                    }
+                }
+            float acc[NT][4];
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                acc[nt][0] = acc[nt][2] = bb[nt][0];
+                acc[nt][1] = acc[nt][3] = bb[nt][1];
+#pragma unroll
+                for (int s = 0; s < 2; ++s) mma_bf16_16816(acc[nt], a[s][0], a[s][1], a[s][2], a[s][3], bw[nt][s][0], bw[nt][s][1]);
+            }
+            // ---- SiLU -> bf16 -> staging [pixel][COUT] ----
+            if (rp > 0) __syncthreads();                    // previous row pair's staging fully stored
+            uint32_t *st = reinterpret_cast<uint32_t *>(stage);
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    const int pix = trow * kStemTW + px0 + g + 8 * r;
+                    st[(pix * COUT + nt * 8 + 2 * t4) >> 1] = pack_bf16x2(silu_f(acc[nt][2 * r]), silu_f(acc[nt][2 * r + 1]));
+                }
+            __syncthreads();
+            constexpr int CPP = COUT / 8;                   // 16-byte chunks per pixel
+            for (int i = threadIdx.x; i < 2 * kStemTW * CPP; i += 256) {
+                const int pix = i / CPP, ch = i % CPP;
+                const int ho = ho0 + 2 * rp + pix / kStemTW, wo = wo0 + pix % kStemTW;
+                if (ho < Ho && wo < Wo)
+                    stg16(out + (((size_t)b * Ho + ho) * Wo + wo) * out_cs + out_off + ch * 8, reinterpret_cast<const uint4 *>(stage)[i]);
+            }
+        }
+        __syncthreads();                                    // this buffer / staging are free for the next iteration
     }
 }
 
@@ -316,15 +411,27 @@ inline int grid_for(size_t total, int block) {
 
 }  // namespace
 
+template <int COUT>
+void stem_launch_t(const float *img, const float *w27, const float *bias, __nv_bfloat16 *out, int out_cs, int out_off, int B, int H,
+                   int W, cudaStream_t st) {
+    const long tiles = (long)B * cdiv(H / 2, kStemTH) * cdiv(W / 2, kStemTW);
+    const size_t smem = (size_t)2 * kStemPatchFloats * 4 + (size_t)2 * kStemTW * COUT * 2;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(stem_kernel<COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        attr_set = true;
+    }
+    const int grid = (int)std::min<long>(tiles, (long)kNumSMs * 2);
+    launch_pdl(stem_kernel<COUT>, dim3(grid), dim3(256), smem, st, img, w27, bias, out, B, H, W, out_cs, out_off);
+}
+
 int stem_launch(const float *img, const float *w27, const float *bias, __nv_bfloat16 *out, int out_cs, int out_off,
                 int cout, int B, int H, int W, cudaStream_t st) {
-    const size_t total = (size_t)B * (H / 2) * (W / 2);
-    const int grid = grid_for(total, 128);
     switch (cout) {
-        case 16: launch_pdl(stem_kernel<16>, dim3(grid), dim3(128), 0, st, img, w27, bias, out, B, H, W, out_cs, out_off); break;
-        case 32: launch_pdl(stem_kernel<32>, dim3(grid), dim3(128), 0, st, img, w27, bias, out, B, H, W, out_cs, out_off); break;
-        case 48: launch_pdl(stem_kernel<48>, dim3(grid), dim3(128), 0, st, img, w27, bias, out, B, H, W, out_cs, out_off); break;
-        case 64: launch_pdl(stem_kernel<64>, dim3(grid), dim3(128), 0, st, img, w27, bias, out, B, H, W, out_cs, out_off); break;
+        case 16: stem_launch_t<16>(img, w27, bias, out, out_cs, out_off, B, H, W, st); break;
+        case 32: stem_launch_t<32>(img, w27, bias, out, out_cs, out_off, B, H, W, st); break;
+        case 48: stem_launch_t<48>(img, w27, bias, out, out_cs, out_off, B, H, W, st); break;
+        case 64: stem_launch_t<64>(img, w27, bias, out, out_cs, out_off, B, H, W, st); break;
         default: return 1;
     }
     return 0;
