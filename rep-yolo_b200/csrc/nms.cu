@@ -14,6 +14,8 @@
 // double, exactly like torchvision's CPU kernel.
 #include "nms.cuh"
 
+#include <math.h>
+
 #include "common.cuh"
 
 namespace ry {
@@ -230,17 +232,24 @@ __global__ void __launch_bounds__(kSortThreads) sort_scatter_kernel(const uint32
 }
 
 // ---- greedy scan ---------------------------------------------------------------------------------------------------
+// torchvision's CPU kernel suppresses iff (double)ovr > (double)thr with ovr the fp32 quotient.  For a float q,
+// (double)q > thr  <=>  q >= t_up, t_up = the smallest float whose value exceeds thr (computed on the host), so the
+// compare runs in fp32; and when the boxes do not intersect (inter == 0) the quotient is 0, -0 or NaN, never > thr >= 0,
+// so the IEEE division is only paid for overlapping pairs.  `nonneg` = (thr >= 0).
+struct IouThr { float t_up; int nonneg; };
+
 __device__ __forceinline__ bool iou_gt(float ax1, float ay1, float ax2, float ay2, float aa, float bx1, float by1, float bx2,
-                                       float by2, float ba, double thr) {
+                                       float by2, float ba, IouThr thr) {
     const float xx1 = fmaxf(ax1, bx1), yy1 = fmaxf(ay1, by1), xx2 = fminf(ax2, bx2), yy2 = fminf(ay2, by2);
     const float w = fmaxf(__fsub_rn(xx2, xx1), 0.0f), h = fmaxf(__fsub_rn(yy2, yy1), 0.0f);
     const float inter = __fmul_rn(w, h);
+    if (inter == 0.0f && thr.nonneg) return false;
     const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(aa, ba), inter));
-    return (double)ovr > thr;
+    return ovr >= thr.t_up;
 }
 
 __global__ void __launch_bounds__(kChunk) nms_scan_kernel(const float *__restrict__ rows, const uint32_t *__restrict__ order,
-                                                          const int *__restrict__ counts, size_t cap, double iou_thr,
+                                                          const int *__restrict__ counts, size_t cap, IouThr iou_thr,
                                                           int agnostic, int max_det, int max_nms, float *__restrict__ out,
                                                           int *__restrict__ out_counts) {
     extern __shared__ unsigned char smraw[];
@@ -399,7 +408,15 @@ int nms_run(const float *pred, int B, int N, int nc, float conf, double iou, con
         cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr_set = true;
     }
-    nms_scan_kernel<<<B, kChunk, smem, st>>>(rows, i0, cnt, L.cap, iou, agnostic, max_det, max_nms, out, counts);
+    IouThr thr;
+    {   // smallest float strictly greater than the double threshold
+        float tf = (float)iou;
+        if (!((double)tf > iou)) tf = nextafterf(tf, INFINITY);
+        else while ((double)nextafterf(tf, -INFINITY) > iou) tf = nextafterf(tf, -INFINITY);
+        thr.t_up = tf;
+        thr.nonneg = iou >= 0.0 ? 1 : 0;
+    }
+    nms_scan_kernel<<<B, kChunk, smem, st>>>(rows, i0, cnt, L.cap, thr, agnostic, max_det, max_nms, out, counts);
     RY_CUDA(cudaGetLastError());
     return 0;
 }
