@@ -74,3 +74,28 @@ def test_conv_vs_torch(case):
         mask[dst2[1]:dst2[1] + dst2[2]] = False
     if mask.any():
         assert bool((full[..., mask] == 7.0).all())
+
+
+def test_multi_source_1x1_conv():
+    """1x1 conv over the channel concatenation of three separate tensors (DER_Block.cv1 without the torch.cat)."""
+    import repyolo_b200 as R
+    from gpu_util import N, planner, nchw_to_arena, arena_to_nchw
+    g = torch.Generator().manual_seed(77)
+    B, H, W, cs, cout = 2, 32, 32, (48, 24, 48), 48
+    cin = sum(cs)
+    w = torch.randn(cout, cin, 1, 1, generator=g) / cin ** 0.5
+    b = torch.randn(cout, generator=g) * 0.5
+    xs = [torch.randn(B, c, H, W, generator=g) for c in cs]
+    P = planner.Plan()
+    tins = [P.full(P.tensor(c, 0)) for c in cs]
+    dst = P.full(P.tensor(cout, 0))
+    P.conv(0, w, b, tins, dst)
+    eng = R.NativeEngine(P, 1, 'cuda:0')
+    eng.bind(B, H, W)
+    for v, x in zip(tins, xs):
+        nchw_to_arena(eng, v, x)
+    eng.run_ops(0, 1)
+    torch.cuda.synchronize()
+    got = arena_to_nchw(eng, dst)
+    ref = F.silu(F.conv2d(torch.cat(xs, 1).bfloat16().float(), w.bfloat16().float(), b))
+    assert float((got - ref).norm() / ref.norm()) < 4e-3

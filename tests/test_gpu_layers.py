@@ -139,3 +139,42 @@ def test_forward_then_nms_matches_oracle_nms():
         ref = nms_oracle.non_max_suppression(pred.cpu(), conf, iou)
         for a, b in zip(got, ref):
             assert a.shape == b.shape and a.cpu().numpy().tobytes() == b.numpy().tobytes()
+
+
+def test_config4_1280_runs_and_nms_matches():
+    """BASELINE config 4 shape (1280x1280: 160/80/40 maps, 100800 candidates): the whole path runs, output is finite,
+    and NMS on the GPU candidates is bit-exact against the oracle NMS."""
+    import repyolo_b200 as R
+    from oracle import nms_oracle
+    layers, save, sd, fz = O.make_model(seed=0, mode='calibrated')
+    m = R.Model()
+    m.load_state_dict(sd, strict=True)
+    m.fuse()
+    x = torch.rand(1, 3, 1280, 1280, generator=torch.Generator().manual_seed(11))
+    pred, raws = m(x.cuda())
+    assert pred.shape == (1, 100800, 6) and bool(torch.isfinite(pred).all())
+    assert raws[0].shape == (1, 3, 160, 160, 6)
+    got = R.non_max_suppression(pred, 0.25, 0.45)
+    ref = nms_oracle.non_max_suppression(pred.cpu(), 0.25, 0.45)
+    for a, b in zip(got, ref):
+        assert a.shape == b.shape and a.cpu().numpy().tobytes() == b.numpy().tobytes()
+
+
+def test_default_init_teacher_forced_1280_der_block():
+    """DER_Block L1 at 1280x1280 (640^2 maps, halo tiles + multi-source cv1) against the oracle, teacher-forced."""
+    import repyolo_b200 as R
+    from gpu_util import nchw_to_arena, arena_to_nchw, rel_l2
+    layers, save, sd, fz = O.make_model(seed=0, mode='calibrated')
+    m = R.Model()
+    m.load_state_dict(sd, strict=True)
+    m.fuse()
+    eng = m.engine('cuda:0')
+    eng.bind(1, 1280, 1280)
+    g = [gr for gr in eng.plan_ir.groups if gr.layers[0] == 1][0]
+    x_in = torch.randn(1, 48, 640, 640, generator=torch.Generator().manual_seed(5)).abs()
+    nchw_to_arena(eng, g.inputs[0][1], x_in)
+    eng.run_ops(g.first_op, g.last_op)
+    torch.cuda.synchronize()
+    got = arena_to_nchw(eng, g.output)
+    ref = O.run_fused_layer(fz, layers[1], x_in.bfloat16().float())
+    assert rel_l2(got, ref) <= 3e-2
