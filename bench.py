@@ -218,18 +218,38 @@ def run_native(args):
             per_op[j] += t
     eng.set_profiling(False)
     conv_flops = 0.0
+    pk = peaks()
+    ridge = pk['tf_sustained'] * 1e12 / (pk['hbm'] * 1e9)          # FLOP per HBM byte at which a conv turns tensor-bound
+    cls = {'tensor': [0.0, 0.0, 0.0, 0], 'hbm': [0.0, 0.0, 0.0, 0]}  # [flops, bytes, ms, launches]
     for j, d in enumerate(ops):
         all_ms += per_op[j]
         if d.kind in (2, 11):        # RY_OP_CONV, RY_OP_DETECT -> conv_umma_kernel
             conv_ms += per_op[j]
             lvl = eng.plan_ir.tensors[d.in0.tensor].level
-            ho, wo = (S >> lvl) // d.stride, (S >> lvl) // d.stride
-            conv_flops += 2.0 * d.cout * d.cin * d.ksize * d.ksize * ho * wo * B
+            hi, wi = S >> lvl, S >> lvl
+            ho, wo = hi // d.stride, wi // d.stride
+            fl = 2.0 * d.cout * d.cin * d.ksize * d.ksize * ho * wo * B
+            by = 2.0 * B * (hi * wi * d.cin + ho * wo * d.cout) if d.kind == 2 else B * (2.0 * hi * wi * d.cin + 8.0 * ho * wo * d.cout)
+            conv_flops += fl
+            c = cls['tensor' if fl / by >= ridge else 'hbm']
+            c[0] += fl; c[1] += by; c[2] += per_op[j]; c[3] += 1
     conv_ms /= prof_steps
     all_ms /= prof_steps
     n_conv = sum(1 for d in ops if d.kind in (2, 11))
-    pk = peaks()
     achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+    detail = {}
+    for name, (fl, by, t, n) in cls.items():
+        t /= prof_steps
+        if n and t > 0:
+            detail[name + '_bound_layers'] = {
+                'launches': n, 'ms_per_step': t, 'tflops': fl / (t * 1e-3) / 1e12, 'frac_of_bf16_peak': fl / (t * 1e-3) / 1e12 / pk['tf_sustained'],
+                'algorithmic_gbytes_per_s': by / (t * 1e-3) / 1e9, 'frac_of_hbm_peak': by / (t * 1e-3) / 1e9 / pk['hbm']}
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, 'profiles', 'conv_traffic.json')
+    if os.path.exists(tpath):           # dram__bytes_read+write per conv launch from the committed ncu capture of this workload
+        tj = json.load(open(tpath))
+        if tj.get('batch') == B and tj.get('size') == S:
+            traffic, traffic_src = tj.get('dram_bytes_per_launch'), tj.get('source')
 
     tm = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
     if world > 1:
@@ -247,11 +267,13 @@ def run_native(args):
                         'pipeline': 'H2D of batch i+1 overlaps compute of batch i (2 pinned buffers, copy stream)'},
                 'gpu_launches': launches_per_step * args.steps,
                 'roofline': {'bound': 'tensor', 'kernel': 'conv_umma_kernel', 'achieved': achieved, 'peak': pk['tf_sustained'],
-                             'unit': 'TFLOP/s', 'frac': achieved / pk['tf_sustained'], 'traffic': None,
+                             'unit': 'TFLOP/s', 'frac': achieved / pk['tf_sustained'], 'traffic': traffic, 'traffic_source': traffic_src,
                              'peak_source': f"bf16_tflops_sustained of {pk['src']} (kernel timed inside a long step)",
                              'launches_per_step': n_conv, 'avg_launch_ms': conv_ms / max(n_conv, 1),
                              'conv_ms_per_step': conv_ms, 'all_ops_ms_per_step': all_ms,
-                             'algorithmic_gflop_per_image': conv_flops / B / 1e9},
+                             'algorithmic_gflop_per_image': conv_flops / B / 1e9,
+                             'algorithmic_bytes_per_launch': sum(c[1] for c in cls.values()) / max(n_conv, 1),
+                             'ridge_flop_per_byte': ridge, 'detail': detail},
                 'cpu_baseline': None}
         if world == 1 and not args.no_cpu_baseline:
             from oracle import nms_oracle
