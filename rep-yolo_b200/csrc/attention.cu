@@ -79,13 +79,19 @@ __device__ __forceinline__ float v_of(float x, float wv, float bv, float s1, flo
     return relu6_f(fmaf(s1, silu_f(fmaf(wv, x, bv)), t1));
 }
 
-// One line per CTA, one 16-row query tile per warp.  NT = LP / 8 (compile time: register arrays).
-template <int MODE, int NT>
-__global__ void __launch_bounds__(NT * 16) attn_mma_kernel(const AttnParams p, const Geom gm) {
+// LPC lines per CTA (short lines share a CTA for occupancy), one 16-row query tile per warp.  NT = LP / 8 (compile time:
+// register arrays).  Each line slot is an independent "virtual CTA" of NT*16 threads; only __syncthreads is shared.
+template <int MODE, int NT, int LPC>
+__global__ void __launch_bounds__(NT * 16 * LPC) attn_mma_kernel(const AttnParams p, const Geom gm, int total_lines, size_t slot_bytes) {
     pdl_trigger();
     pdl_wait();
-    extern __shared__ __align__(16) uint8_t sm_raw[];
+    extern __shared__ __align__(16) uint8_t sm_all[];
     constexpr int LP = NT * 8;
+    constexpr int kThreads = NT * 16;                        // threads per line slot
+    const int slot = threadIdx.x / kThreads, tis = threadIdx.x - slot * kThreads;
+    const int vb = blockIdx.x * LPC + slot;                  // global line index
+    const bool active = vb < total_lines;
+    uint8_t *sm_raw = sm_all + (size_t)slot * slot_bytes;
     const int L = gm.L, C = p.C, Cq = p.Cq, KQ = gm.KQ;
     const int sq = gm.sq, sv = gm.sv, sp = gm.sp;
     __nv_bfloat16 *Aq = reinterpret_cast<__nv_bfloat16 *>(sm_raw);
@@ -93,37 +99,42 @@ __global__ void __launch_bounds__(NT * 16) attn_mma_kernel(const AttnParams p, c
     __nv_bfloat16 *Vs = (MODE == MODE_VPV) ? Aq : Bk + (size_t)LP * sq;      // value pass has no q/k operands
     __nv_bfloat16 *Ps = (MODE == MODE_VE) ? Vs : Vs + (size_t)LP * sv;        // energy pass has no V / P
     const int lines = (MODE == MODE_ROW) ? p.H : p.W;
-    const int b = blockIdx.x / lines, line = blockIdx.x % lines;
+    const int b = (active ? vb : 0) / lines, line = (active ? vb : 0) % lines;
     const size_t img = (size_t)b * p.H * p.W;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = tis >> 5, lane = tis & 31;
     const int g = lane >> 2, t4 = lane & 3;
     auto pix_of = [&](int i) -> size_t {       // pixel of line position i
         return (MODE == MODE_ROW) ? img + (size_t)line * p.W + i : img + (size_t)i * p.W + line;
     };
 
     // ---- stage operands ----
-    if (MODE != MODE_VPV) {
+    if (MODE != MODE_VPV && active) {
         // Aq row = [Qhi | Qhi | Qlo | 0], Bk row = [Khi | Klo | Khi | 0]  ->  Aq.Bk^T = Qhi.Khi + Qhi.Klo + Qlo.Khi
-        for (int idx = threadIdx.x; idx < LP * KQ; idx += blockDim.x) {
-            const int pi = idx / KQ, col = idx - pi * KQ;
+        const __nv_bfloat16 zero = __float2bfloat16_rn(0.0f);
+        for (int idx = tis; idx < LP * Cq; idx += kThreads) {            // each q / k element is read once
+            const int pi = idx / Cq, d = idx - pi * Cq;
             float qa = 0.0f, kb = 0.0f;
-            int sec = 3;
-            if (pi < L && col < 3 * Cq) {
-                sec = col / Cq;
-                const int d = col - sec * Cq;
+            if (pi < L) {
                 const size_t px = pix_of(pi);
                 qa = __ldg(p.q + px * Cq + d);
                 kb = __ldg(p.k + px * Cq + d);
             }
             const __nv_bfloat16 qh = __float2bfloat16_rn(qa), kh = __float2bfloat16_rn(kb);
             const __nv_bfloat16 ql = __float2bfloat16_rn(qa - __bfloat162float(qh)), kl = __float2bfloat16_rn(kb - __bfloat162float(kh));
-            Aq[(size_t)pi * sq + col] = sec == 2 ? ql : qh;
-            Bk[(size_t)pi * sq + col] = sec == 1 ? kl : kh;
+            __nv_bfloat16 *ar = Aq + (size_t)pi * sq, *br = Bk + (size_t)pi * sq;
+            ar[d] = qh; ar[Cq + d] = qh; ar[2 * Cq + d] = ql;
+            br[d] = kh; br[Cq + d] = kl; br[2 * Cq + d] = kh;
+        }
+        const int padc = KQ - 3 * Cq;
+        for (int idx = tis; idx < LP * padc; idx += kThreads) {
+            const int pi = idx / padc, col = 3 * Cq + idx - pi * padc;
+            Aq[(size_t)pi * sq + col] = zero;
+            Bk[(size_t)pi * sq + col] = zero;
         }
     }
-    if (MODE != MODE_VE) {
+    if (MODE != MODE_VE && active) {
         const int vecs = C / 8;
-        for (int idx = threadIdx.x; idx < LP * vecs; idx += blockDim.x) {
+        for (int idx = tis; idx < LP * vecs; idx += kThreads) {
             const int pi = idx / vecs, c = (idx - pi * vecs) * 8;
             uint4 o = make_uint4(0, 0, 0, 0);
             if (pi < L) {
@@ -142,11 +153,11 @@ __global__ void __launch_bounds__(NT * 16) attn_mma_kernel(const AttnParams p, c
             *reinterpret_cast<uint4 *>(Vs + (size_t)pi * sv + c) = o;
         }
     }
-    if (MODE == MODE_VPV) {
+    if (MODE == MODE_VPV && active) {
         // P[j][k] = E[b][i = line][j][k] (bf16 scratch written by the energy pass), rows j >= L are zero
         const __nv_bfloat16 *E = reinterpret_cast<const __nv_bfloat16 *>(p.scratch) + ((size_t)b * p.H + line) * p.W * LP;
         const int vecs = LP / 8;
-        for (int idx = threadIdx.x; idx < LP * vecs; idx += blockDim.x) {
+        for (int idx = tis; idx < LP * vecs; idx += kThreads) {
             const int j = idx / vecs, c = (idx - j * vecs) * 8;
             uint4 o = make_uint4(0, 0, 0, 0);
             if (j < L) o = __ldg(reinterpret_cast<const uint4 *>(E + (size_t)j * LP + c));
@@ -154,6 +165,7 @@ __global__ void __launch_bounds__(NT * 16) attn_mma_kernel(const AttnParams p, c
         }
     }
     __syncthreads();
+    if (!active) return;
 
     const int row0 = warp * 16;                                  // this warp's query rows
     float m_row[2] = {0.0f, 0.0f}, s_row[2] = {1.0f, 1.0f};
@@ -286,6 +298,7 @@ int pick_nt(int L) {
 
 template <int MODE, int NT>
 int launch_nt(const AttnParams &p, int L, cudaStream_t st) {
+    constexpr int LPC = NT <= 4 ? 4 : (NT <= 8 ? 2 : 1);      // lines per CTA: keep CTAs at >= 4 warps
     Geom gm;
     gm.L = L;
     gm.LP = NT * 8;
@@ -296,14 +309,16 @@ int launch_nt(const AttnParams &p, int L, cudaStream_t st) {
     size_t smem = 0;
     if (MODE != MODE_VPV) smem += 2 * (size_t)gm.LP * gm.sq * 2;
     if (MODE != MODE_VE) smem += (size_t)gm.LP * gm.sv * 2 + (size_t)gm.LP * gm.sp * 2;
-    if (smem > 227 * 1024) return 1;
+    smem = (smem + 15) & ~size_t(15);
+    if (smem * LPC > 227 * 1024) return 1;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(attn_mma_kernel<MODE, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(attn_mma_kernel<MODE, NT, LPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         attr_set = true;
     }
     const int lines = (MODE == MODE_ROW) ? p.H : p.W;
-    launch_pdl(attn_mma_kernel<MODE, NT>, dim3(p.B * lines), dim3(NT * 16), smem, st, p, gm);
+    const int total = p.B * lines;
+    launch_pdl(attn_mma_kernel<MODE, NT, LPC>, dim3((total + LPC - 1) / LPC), dim3(NT * 16 * LPC), smem * LPC, st, p, gm, total, smem);
     return 0;
 }
 
