@@ -223,19 +223,25 @@ def run_native(args):
     cls = {'tensor': [0.0, 0.0, 0.0, 0], 'hbm': [0.0, 0.0, 0.0, 0]}  # [flops, bytes, ms, launches]
     for j, d in enumerate(ops):
         all_ms += per_op[j]
-        if d.kind in (2, 11):        # RY_OP_CONV, RY_OP_DETECT -> conv_umma_kernel
+        if d.kind in (2, 11, 12):    # RY_OP_CONV, RY_OP_DETECT (conv_umma_kernel), RY_OP_CONV_CHAIN (conv_chain_kernel)
             conv_ms += per_op[j]
             lvl = eng.plan_ir.tensors[d.in0.tensor].level
             hi, wi = S >> lvl, S >> lvl
             ho, wo = hi // d.stride, wi // d.stride
             fl = 2.0 * d.cout * d.cin * d.ksize * d.ksize * ho * wo * B
             by = 2.0 * B * (hi * wi * d.cin + ho * wo * d.cout) if d.kind == 2 else B * (2.0 * hi * wi * d.cin + 8.0 * ho * wo * d.cout)
+            if d.kind == 12:          # fused chain: all stages' MACs; bytes = input + the outputs that are actually stored
+                prev, outs = d.cout, [d.out0, d.out1, d.out2]
+                by = 2.0 * B * hi * wi * d.cin + sum(2.0 * B * hi * wi * o.c_len for o in outs if o.tensor >= 0)
+                for i in range(d.n_post):
+                    fl += 2.0 * prev * d.post_cout[i] * hi * wi * B
+                    prev = d.post_cout[i]
             conv_flops += fl
             c = cls['tensor' if fl / by >= ridge else 'hbm']
             c[0] += fl; c[1] += by; c[2] += per_op[j]; c[3] += 1
     conv_ms /= prof_steps
     all_ms /= prof_steps
-    n_conv = sum(1 for d in ops if d.kind in (2, 11))
+    n_conv = sum(1 for d in ops if d.kind in (2, 11, 12))
     achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
     detail = {}
     for name, (fl, by, t, n) in cls.items():
@@ -266,7 +272,7 @@ def run_native(args):
                         'd2h_bytes_per_step': B * world * (300 * 6 * 4 + 4), 'ms_per_step': ms_e2e / args.steps,
                         'pipeline': 'H2D of batch i+1 overlaps compute of batch i (2 pinned buffers, copy stream)'},
                 'gpu_launches': launches_per_step * args.steps,
-                'roofline': {'bound': 'tensor', 'kernel': 'conv_umma_kernel', 'achieved': achieved, 'peak': pk['tf_sustained'],
+                'roofline': {'bound': 'tensor', 'kernel': 'conv_umma_kernel (+ conv_chain_kernel: fused 3x3->1x1 chains of the same design)', 'achieved': achieved, 'peak': pk['tf_sustained'],
                              'unit': 'TFLOP/s', 'frac': achieved / pk['tf_sustained'], 'traffic': traffic, 'traffic_source': traffic_src,
                              'peak_source': f"bf16_tflops_sustained of {pk['src']} (kernel timed inside a long step)",
                              'launches_per_step': n_conv, 'avg_launch_ms': conv_ms / max(n_conv, 1),

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define RY_ABI_VERSION 2
+#define RY_ABI_VERSION 3
 
 typedef struct ry_plan ry_plan;
 
@@ -69,7 +69,9 @@ enum ry_op_kind {
     RY_OP_ATTN_QK = 8,    /* grouped 1x1 q/k convs + SiLU + shared BN + ReLU6 -> fp32 q,k         (attention q/k)   */
     RY_OP_CRISSCROSS = 9, /* CrissCrossAttention core: gamma*out + x                                                */
     RY_OP_VERTICAL = 10,  /* VerticalAttention core:   gamma*out + x                                                */
-    RY_OP_DETECT = 11     /* head 1x1 conv on tcgen05 + sigmoid/grid/anchor decode -> pred + raw  (IDetect)         */
+    RY_OP_DETECT = 11,    /* head 1x1 conv on tcgen05 + sigmoid/grid/anchor decode -> pred + raw  (IDetect)         */
+    RY_OP_CONV_CHAIN = 12 /* 3x3 s1 conv -> 1x1 conv [-> 1x1 conv] fused in one kernel (small-channel DER_Block stages,    */
+                          /* common.py:3646-3651): out0/out1/out2 = optional stores of stage 0/1/2 (tensor -1 = on-chip only) */
 };
 
 enum ry_act { RY_ACT_NONE = 0, RY_ACT_SILU = 1 };
@@ -92,6 +94,10 @@ typedef struct ry_op_desc {
     int32_t level_idx;     /* DETECT: pyramid level (row offset / stride / anchors) */
     int32_t n_src;         /* CONV: number of concatenated input views (0 or 1 = just in0) */
     int32_t pad_;
+    int32_t n_post;        /* CONV_CHAIN: number of fused 1x1 stages (1 or 2); their weights/biases are aux_off[0..3]     */
+    int32_t post_cout[2];  /*   = {w1, b1, w2, b2} (fp32 [cout_s][cin_s], [cout_s]), cin_s = previous stage's cout          */
+    int32_t post_act[2];   /*   ry_act of each fused stage */
+    int32_t pad2_;
     int64_t w_off;         /* byte offsets into the host weight blob; -1 = none.                                    */
     int64_t b_off;         /*   CONV/STEM/DETECT: w = fp32 [cout][cin][k][k] (PyTorch OIHW), b = fp32 [cout]        */
     int64_t aux_off[6];    /*   DW5: w = fp32 [C][5][5]; CA: w = f1 [C/16][C], aux0 = f2 [C][C/16];                 */

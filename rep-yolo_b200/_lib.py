@@ -11,7 +11,7 @@ RY_BF16, RY_F32 = 0, 1
 T_MAP, T_VEC, T_EXTERNAL = 0, 1, 2
 X_IMAGE, X_PRED, X_RAW0 = 0, 1, 2
 (OP_STEM, OP_CONV, OP_DW5, OP_MAXPOOL2, OP_SPP, OP_UPSAMPLE2, OP_CA, OP_ATTN_QK, OP_CRISSCROSS, OP_VERTICAL,
- OP_DETECT) = range(1, 12)
+ OP_DETECT, OP_CONV_CHAIN) = range(1, 13)
 ACT_NONE, ACT_SILU = 0, 1
 
 
@@ -28,7 +28,8 @@ class OpDesc(C.Structure):
     _fields_ = [('kind', C.c_int32), ('layer', C.c_int32),
                 ('in0', View), ('in1', View), ('in2', View), ('out0', View), ('out1', View), ('out2', View),
                 ('ksize', C.c_int32), ('stride', C.c_int32), ('act', C.c_int32), ('cin', C.c_int32), ('cout', C.c_int32),
-                ('level_idx', C.c_int32), ('n_src', C.c_int32), ('pad_', C.c_int32), ('w_off', C.c_int64), ('b_off', C.c_int64), ('aux_off', C.c_int64 * 6),
+                ('level_idx', C.c_int32), ('n_src', C.c_int32), ('pad_', C.c_int32), ('n_post', C.c_int32), ('post_cout', C.c_int32 * 2),
+                ('post_act', C.c_int32 * 2), ('pad2_', C.c_int32), ('w_off', C.c_int64), ('b_off', C.c_int64), ('aux_off', C.c_int64 * 6),
                 ('fparam', C.c_float * 8)]
 
 
@@ -72,7 +73,7 @@ def lib():
     for name in EXPORTS:
         if name not in ('ry_last_error', 'ry_plan_destroy', 'ry_abi_version', 'ry_abi_sizeof'):
             getattr(L, name).restype = i32
-    if L.ry_abi_version() != 2:
+    if L.ry_abi_version() != 3:
         raise NativeError('ABI version mismatch between _lib.py and librepyolo_b200.so')
     L.ry_abi_sizeof.argtypes = [i32]
     L.ry_abi_sizeof.restype = i32

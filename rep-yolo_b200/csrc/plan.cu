@@ -17,6 +17,7 @@
 #include "../../include/repyolo_b200.h"
 #include "common.cuh"
 #include "conv_umma.cuh"
+#include "conv_chain.cuh"
 #include "memops.cuh"
 #include "nms.cuh"
 
@@ -63,6 +64,9 @@ struct Op {
     size_t dev[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // device weight-buffer offsets of the op's parameter arrays
     // shape-dependent (filled by bind)
     ConvArgs ca;
+    ChainArgs ch;
+    size_t post_w_dev[2] = {0, 0}, post_b_dev[2] = {0, 0};   // CONV_CHAIN: pre-swizzled 1x1 weight images / padded biases
+    int post_kb[2] = {0, 0}, post_n[2] = {0, 0}, post_wbytes[2] = {0, 0};
     int grid = 0;
     int tmap_first = -1, n_amaps = 1;
     int launches = 0;
@@ -155,6 +159,31 @@ int pack_conv(const ry_op_desc &d, const unsigned char *host, size_t host_bytes,
     for (int co = 0; co < cout; ++co) bp[co] = b[co];
     cp.w_dev = blob.add(wp.data(), wp.size() * sizeof(__nv_bfloat16));
     cp.b_dev = blob.add(bp.data(), bp.size() * sizeof(float));
+    return 0;
+}
+
+// CONV_CHAIN 1x1 stage: weights [cout][cin] fp32 -> bf16 image [N][kb] in the K-major 64/128-byte-swizzled layout the
+// tcgen05 B operand expects in shared memory (a plain bulk copy brings it in); bias padded with zeros to N.
+int pack_post(const unsigned char *host, size_t host_bytes, int64_t w_off, int64_t b_off, int cin, int cout, Blob &blob, Op &op, int i) {
+    if (cin % 8 || cout % 8 || cin > 64 || cout > 64) RY_FAIL("conv chain: fused 1x1 stages need cin, cout <= 64 and multiples of 8");
+    if (w_off < 0 || b_off < 0 || (size_t)w_off + (size_t)cout * cin * 4 > host_bytes || (size_t)b_off + (size_t)cout * 4 > host_bytes)
+        RY_FAIL("conv chain: weight offsets out of range");
+    const float *w = reinterpret_cast<const float *>(host + w_off);
+    const float *b = reinterpret_cast<const float *>(host + b_off);
+    const int kb = cin > 32 ? 64 : 32, rb = kb * 2, N = (cout + 15) / 16 * 16;
+    const uint32_t m = rb == 128 ? 7u : 3u;
+    std::vector<__nv_bfloat16> img((size_t)N * kb, __float2bfloat16(0.0f));
+    for (int n = 0; n < cout; ++n)
+        for (int k = 0; k < cin; ++k) {
+            uint32_t lin = (uint32_t)n * rb + (uint32_t)(k / 8) * 16;
+            lin ^= ((lin >> 7) & m) << 4;
+            img[(lin >> 1) + (k % 8)] = __float2bfloat16_rn(w[(size_t)n * cin + k]);
+        }
+    std::vector<float> bp(N, 0.0f);
+    for (int n = 0; n < cout; ++n) bp[n] = b[n];
+    op.post_w_dev[i] = blob.add(img.data(), img.size() * sizeof(__nv_bfloat16));
+    op.post_b_dev[i] = blob.add(bp.data(), bp.size() * sizeof(float));
+    op.post_kb[i] = kb; op.post_n[i] = N; op.post_wbytes[i] = N * rb;
     return 0;
 }
 
@@ -432,6 +461,82 @@ int bind_conv(ry_plan *p, Op &op, std::vector<CUtensorMap> &maps) {
     return 0;
 }
 
+// Shape-dependent part of a CONV_CHAIN op.
+int bind_chain(ry_plan *p, Op &op, std::vector<CUtensorMap> &maps) {
+    const ry_op_desc &d = op.d;
+    const ConvPacked &cp = op.cp;
+    const Tensor &tin = p->tensors[d.in0.tensor];
+    const int H = tin.h, W = tin.w, B = p->B;
+    if (W % kHaloTw != 0) RY_FAIL("conv chain: map width must be a multiple of 8");
+    if (cp.cblk != 1 || cp.n_ntiles != 1) RY_FAIL("conv chain: the 3x3 stage needs cin, cout <= 64");
+    ChainArgs &a = op.ch;
+    memset(&a, 0, sizeof(a));
+    a.n_stages = 1 + d.n_post;
+    a.kb = cp.kb;
+    a.halo_w = kHaloTw + 2;
+    a.tiles_w = W / kHaloTw; a.tiles_h = cdiv(H, kHaloTh); a.tiles_n = B;
+    auto magic = [](int dd) -> uint32_t { return dd <= 1 ? 0u : (uint32_t)(((1ull << 32) + (uint64_t)dd - 1) / (uint64_t)dd); };
+    a.div_tw = magic(a.tiles_w); a.div_th = magic(a.tiles_h);
+    if ((long)a.tiles_w * a.tiles_h * a.tiles_n >= (1L << 20)) RY_FAIL("conv chain: too many tiles");
+    const ry_view *outs[3] = {&d.out0, &d.out1, &d.out2};
+    int prev = d.cout;
+    for (int s = 0; s < a.n_stages; ++s) {
+        ChainStage &st = a.stage[s];
+        st.ncol = s == 0 ? d.cout : d.post_cout[s - 1];
+        st.N = s == 0 ? cp.BN : op.post_n[s - 1];
+        st.act = s == 0 ? d.act : d.post_act[s - 1];
+        st.store = outs[s]->tensor >= 0 ? 1 : 0;
+        st.chan = outs[s]->c_off;
+        st.swz = st.ncol == 64 ? 7 : (st.ncol == 32 ? 3 : (st.ncol == 16 ? 1 : 0));
+        st.kb_next = s + 1 < a.n_stages ? op.post_kb[s] : 0;
+        st.ks = s == 0 ? cp.ksteps_last : (prev + 15) / 16;
+        if (s > 0) {
+            st.w_bytes = op.post_wbytes[s - 1];
+            st.w_img = p->d_weights + op.post_w_dev[s - 1];
+            st.bias = wf(p, op.post_b_dev[s - 1]);
+        } else {
+            st.bias = wf(p, cp.b_dev);
+        }
+        if (st.store && outs[s]->c_len != st.ncol) RY_FAIL("conv chain: store view width does not match the stage");
+        prev = st.ncol;
+    }
+    if (chain_plan_smem(a)) RY_FAIL("conv chain: shared memory / TMEM plan failed");
+    op.tmap_first = (int)maps.size();
+    const size_t esz = 2;
+    CUtensorMap m;
+    {
+        const cuuint64_t ctot = (cuuint64_t)tin.d.channels;
+        const cuuint64_t dims[4] = {(cuuint64_t)d.cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+        const cuuint64_t str[3] = {ctot * esz, (cuuint64_t)W * ctot * esz, (cuuint64_t)H * W * ctot * esz};
+        const cuuint32_t box[4] = {(cuuint32_t)cp.kb, (cuuint32_t)(kHaloTw + 2), (cuuint32_t)(kHaloTh + 2), 1};
+        if (encode_map(&m, bf(p, d.in0.tensor) + d.in0.c_off, 4, dims, str, box, cp.kb, d.in0.c_len == tin.d.channels)) return 1;
+        maps.push_back(m);
+    }
+    {
+        const cuuint64_t dims[2] = {(cuuint64_t)cp.k_pad, (cuuint64_t)cp.cout_pad};
+        const cuuint64_t str[1] = {(cuuint64_t)cp.k_pad * esz};
+        const cuuint32_t box[2] = {(cuuint32_t)cp.kb, (cuuint32_t)cp.BN};
+        if (encode_map(&m, p->d_weights + cp.w_dev, 2, dims, str, box, cp.kb)) return 1;
+        maps.push_back(m);
+    }
+    for (int s = 0; s < a.n_stages; ++s) {          // one map slot per stage (unused slots repeat the weight map)
+        if (a.stage[s].store) {
+            const Tensor &to = p->tensors[outs[s]->tensor];
+            if (to.h != H || to.w != W) RY_FAIL("conv chain: output tensor level mismatch");
+            const cuuint64_t oc = (cuuint64_t)to.d.channels;
+            const cuuint64_t dims[4] = {oc, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+            const cuuint64_t str[3] = {oc * esz, (cuuint64_t)W * oc * esz, (cuuint64_t)H * W * oc * esz};
+            const cuuint32_t box[4] = {(cuuint32_t)a.stage[s].ncol, (cuuint32_t)kHaloTw, (cuuint32_t)kHaloTh, 1};
+            if (encode_map(&m, bf(p, outs[s]->tensor), 4, dims, str, box, a.stage[s].ncol)) return 1;
+        }
+        maps.push_back(m);
+    }
+    const long tiles = (long)a.tiles_w * a.tiles_h * a.tiles_n;
+    op.grid = (int)std::min<long>(tiles, kNumSMs);
+    op.launches = 1;
+    return 0;
+}
+
 int run_op(ry_plan *p, Op &op, const float *image, float *pred, float *raws[3], cudaStream_t st) {
     const ry_op_desc &d = op.d;
     const int B = p->B;
@@ -450,6 +555,14 @@ int run_op(ry_plan *p, Op &op, const float *image, float *pred, float *raws[3], 
             a.wmap = a.amap + op.n_amaps;
             a.omap = a.wmap + 1;
             conv_launch(a, op.grid, st);
+            break;
+        }
+        case RY_OP_CONV_CHAIN: {
+            ChainArgs a = op.ch;
+            a.amap = p->d_tmaps + op.tmap_first;
+            a.wmap = a.amap + 1;
+            a.omap = a.amap + 2;
+            chain_launch(a, op.grid, st);
             break;
         }
         case RY_OP_DETECT: {
@@ -574,11 +687,21 @@ int ry_plan_create(const ry_tensor_desc *tensors, int n_tensors, const ry_op_des
         const ry_op_desc &d = op.d;
         const ry_view *vs[6] = {&d.in0, &d.in1, &d.in2, &d.out0, &d.out1, &d.out2};
         for (int v = 0; v < 6; ++v)
-            if (view_ok(p, *vs[v], v == 0 || v == 3)) { set_error("op " + std::to_string(i) + ": bad tensor view"); rc = 1; }
+            if (view_ok(p, *vs[v], v == 0 || (v == 3 && d.kind != RY_OP_CONV_CHAIN))) { set_error("op " + std::to_string(i) + ": bad tensor view"); rc = 1; }
         if (rc) break;
         switch (d.kind) {
             case RY_OP_CONV:
             case RY_OP_DETECT: rc = pack_conv(d, host, weight_bytes, blob, op.cp); break;
+            case RY_OP_CONV_CHAIN: {
+                if (d.ksize != 3 || d.stride != 1 || d.n_post < 1 || d.n_post > 2) { set_error("conv chain: 3x3 s1 main conv with 1 or 2 fused 1x1 stages"); rc = 1; break; }
+                rc = pack_conv(d, host, weight_bytes, blob, op.cp);
+                int prev = d.cout;
+                for (int i = 0; i < d.n_post && !rc; ++i) {
+                    rc = pack_post(host, weight_bytes, d.aux_off[2 * i], d.aux_off[2 * i + 1], prev, d.post_cout[i], blob, op, i);
+                    prev = d.post_cout[i];
+                }
+                break;
+            }
             case RY_OP_STEM: {
                 if (d.cin != 3 || d.ksize != 3 || d.stride != 2) { set_error("stem: expects 3x3 s2 on 3 channels"); rc = 1; break; }
                 if (d.w_off < 0 || (size_t)d.w_off + (size_t)d.cout * 27 * 4 > weight_bytes) { set_error("stem: weight offset"); rc = 1; break; }
@@ -682,6 +805,7 @@ int ry_plan_bind(ry_plan *p, int B, int H, int W, void *workspace, size_t worksp
         if (op.d.kind == RY_OP_CONV || op.d.kind == RY_OP_DETECT) {
             if (bind_conv(p, op, maps)) return 1;
         }
+        if (op.d.kind == RY_OP_CONV_CHAIN && bind_chain(p, op, maps)) return 1;
         if (op.d.kind == RY_OP_CRISSCROSS || op.d.kind == RY_OP_VERTICAL || op.d.kind == RY_OP_CA) op.launches = 2;
     }
     // Detect rows: level -> anchor -> y -> x (models/yolo.py:152, 166)

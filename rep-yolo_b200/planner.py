@@ -101,12 +101,31 @@ class Plan:
                        b_off=self.blob.add(b))
 
 
+    def chain(self, layer, src, main, posts):
+        """3x3 conv -> 1x1 [-> 1x1] fused (OP_CONV_CHAIN).  main = (w, b, dst|None); posts = [(w, b, act, dst|None), ...]"""
+        w0, b0, dst0 = main
+        cout, cin, k, _ = w0.shape
+        assert k == 3 and src[2] == cin and 1 <= len(posts) <= 2
+        d = self.ops[self.op(N.OP_CONV_CHAIN, layer, in0=src, out0=dst0, out1=posts[0][3], out2=posts[1][3] if len(posts) > 1 else None,
+                             ksize=3, stride=1, act=N.ACT_SILU, cin=cin, cout=cout, w_off=self.blob.add(w0), b_off=self.blob.add(b0),
+                             aux=[o for (w, b, _, _) in posts for o in (self.blob.add(w), self.blob.add(b))])]
+        d.n_post = len(posts)
+        prev = cout
+        for i, (w, b, act, dst) in enumerate(posts):
+            assert w.shape[1] == prev and w.shape[2] == 1 and (dst is None or dst[2] == w.shape[0])
+            d.post_cout[i], d.post_act[i] = w.shape[0], (N.ACT_SILU if act else N.ACT_NONE)
+            prev = w.shape[0]
+
+
 def _gs_perm(c):
     return list(range(0, c, 2)) + list(range(1, c, 2))
 
 
-def lower(layers, fz, nc=1):
+def lower(layers, fz, nc=1, fuse_chains=None):
     """layers: arch.parse() output; fz: fold.fold_state_dict() output.  Returns a Plan."""
+    import os
+    if fuse_chains is None:
+        fuse_chains = os.environ.get('RY_FUSE_CHAINS', '1') != '0'
     P = Plan()
     img = P.tensor(3, 0, N.RY_F32, N.T_EXTERNAL, N.X_IMAGE)
     pred = P.tensor(5 + nc, 0, N.RY_F32, N.T_EXTERNAL, N.X_PRED)
@@ -196,11 +215,19 @@ def lower(layers, fz, nc=1):
             h1, h2 = P.full(P.tensor(c1 // 2, lvl)), P.full(P.tensor(c1 // 2, lvl))
             P.conv(L.i, *W(f'{p}.stage1.0.reparam_conv'), x, x1)
             P.conv(L.i, *W(f'{p}.stage2.0.reparam_conv'), x1, x2)
-            P.conv(L.i, *W(f'{p}.stage3.0.reparam_conv'), x2, x3)
-            for j, (src, stage, dstv) in enumerate(((x3, 4, x41), (x41, 5, x42), (x42, 6, x43))):
-                P.conv(L.i, *W(f'{p}.cv{j}_1.conv'), src, h1)
-                P.conv(L.i, *W(f'{p}.stage{stage}.0.reparam_conv'), h1, h2)
-                P.conv(L.i, *W(f'{p}.cv{j}_2.conv'), h2, dstv)
+            if c1 <= 64 and fuse_chains:
+                # small-channel stages: 3x3 -> 1x1 [-> 1x1] chains in one kernel; x3, x4_2 and the 3x3 outputs stay on chip
+                R, C = (lambda q: W(f'{p}.{q}.0.reparam_conv')), (lambda q: W(f'{p}.{q}.conv'))
+                P.chain(L.i, x2, (*R('stage3'), None), [(*C('cv0_1'), True, h1)])
+                P.chain(L.i, h1, (*R('stage4'), None), [(*C('cv0_2'), True, x41), (*C('cv1_1'), True, h2)])
+                P.chain(L.i, h2, (*R('stage5'), None), [(*C('cv1_2'), True, None), (*C('cv2_1'), True, h1)])
+                P.chain(L.i, h1, (*R('stage6'), None), [(*C('cv2_2'), True, x43)])
+            else:
+                P.conv(L.i, *W(f'{p}.stage3.0.reparam_conv'), x2, x3)
+                for j, (src, stage, dstv) in enumerate(((x3, 4, x41), (x41, 5, x42), (x42, 6, x43))):
+                    P.conv(L.i, *W(f'{p}.cv{j}_1.conv'), src, h1)
+                    P.conv(L.i, *W(f'{p}.stage{stage}.0.reparam_conv'), h1, h2)
+                    P.conv(L.i, *W(f'{p}.cv{j}_2.conv'), h2, dstv)
             dst = out_view(L, lvl)
             P.conv(L.i, *W(f'{p}.cv1.conv'), [x1, x41, x43], dst)
         elif L.kind == 'MP':

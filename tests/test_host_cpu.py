@@ -21,7 +21,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     lib = ctypes.CDLL(so)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.ry_abi_version() == 2
+    assert lib.ry_abi_version() == 3
     N = importlib.import_module('rep-yolo_b200._lib')
     assert sorted(N.EXPORTS) == declared               # the ctypes binding covers the whole header
     assert lib.ry_abi_sizeof(1) == ctypes.sizeof(N.OpDesc) and lib.ry_abi_sizeof(0) == ctypes.sizeof(N.TensorDesc)
@@ -72,7 +72,8 @@ def test_lowering_invariants(oracle_model):
     m.fuse()
     P = planner.lower(m._layers, m._fused, 1)
     kinds = [o.kind for o in P.ops]
-    assert kinds.count(N.OP_CONV) + kinds.count(N.OP_DETECT) + kinds.count(N.OP_STEM) == 130      # dense convs
+    n_chain = sum(1 + o.n_post for o in P.ops if o.kind == N.OP_CONV_CHAIN)                        # fused 3x3 -> 1x1 [-> 1x1]
+    assert kinds.count(N.OP_CONV) + kinds.count(N.OP_DETECT) + kinds.count(N.OP_STEM) + n_chain == 130   # dense convs
     assert kinds.count(N.OP_DW5) == 18 and kinds.count(N.OP_MAXPOOL2) == 6 and kinds.count(N.OP_UPSAMPLE2) == 2
     assert kinds.count(N.OP_CRISSCROSS) == 6 and kinds.count(N.OP_VERTICAL) == 6 and kinds.count(N.OP_CA) == 6
     written = {}
@@ -95,6 +96,12 @@ def test_lowering_invariants(oracle_model):
         if o.kind in (N.OP_CONV, N.OP_DETECT, N.OP_STEM):
             lvl = P.tensors[o.out0.tensor].level if o.kind != N.OP_DETECT else P.tensors[o.in0.tensor].level
             flops += 2 * o.cin * o.cout * o.ksize ** 2 * (640 >> lvl) ** 2
+        elif o.kind == N.OP_CONV_CHAIN:
+            px, prev = (640 >> P.tensors[o.in0.tensor].level) ** 2, o.cout
+            flops += 2 * o.cin * o.cout * 9 * px
+            for i in range(o.n_post):
+                flops += 2 * prev * o.post_cout[i] * px
+                prev = o.post_cout[i]
     assert abs(flops / 1e9 - 68.733) < 0.01            # dense-conv GFLOP / image @640
 
 

@@ -13,7 +13,7 @@ import repyolo_b200 as R  # noqa: E402
 from oracle import repyolo_oracle as O  # noqa: E402  (weights generator only)
 
 KIND = {1: 'stem', 2: 'conv', 3: 'dw5', 4: 'maxpool2', 5: 'spp', 6: 'upsample2', 7: 'ca', 8: 'attn_qk', 9: 'crisscross',
-        10: 'vertical', 11: 'detect'}
+        10: 'vertical', 11: 'detect', 12: 'chain'}
 
 
 def main():
