@@ -33,7 +33,7 @@ typedef struct ry_plan ry_plan;
 
 /* ---- plan IR ------------------------------------------------------------------------------------------------ */
 
-enum ry_dtype { RY_BF16 = 0, RY_F32 = 1 };
+enum ry_dtype { RY_BF16 = 0, RY_F32 = 1, RY_U8 = 2 };
 
 enum ry_tensor_kind {
     RY_T_MAP = 0,      /* activation map, NHWC: [B, H>>level, W>>level, channels] */
@@ -132,6 +132,10 @@ int ry_forward(ry_plan *plan, const float *image, float *pred, float *raw0, floa
 /* Runs ops [first,last) of the bound plan (externals as given; NULL allowed when the range does not touch them). */
 int ry_run_ops(ry_plan *plan, int first, int last, const float *image, float *pred, float *raw0, float *raw1,
                float *raw2, void *stream);
+/* Input image element type of the following ry_forward / ry_run_ops calls: RY_F32 (default, [0,1] as Model.forward takes
+ * it) or RY_U8 (uint8 NCHW 0..255 as detect.py:73-78 ships it to the device; the /255 of detect.py:76 is fused in the stem).
+ * With RY_U8 the `image` argument is reinterpreted as const uint8_t*. */
+int ry_plan_set_image_dtype(ry_plan *plan, int dtype);
 /* Number of kernel launches ry_forward issues for the bound shape (for bench.py's gpu_launches). */
 int ry_plan_launch_count(ry_plan *plan, int *n);
 

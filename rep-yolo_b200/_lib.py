@@ -7,7 +7,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(HERE, 'csrc', 'librepyolo_b200.so')
 
-RY_BF16, RY_F32 = 0, 1
+RY_BF16, RY_F32, RY_U8 = 0, 1, 2
 T_MAP, T_VEC, T_EXTERNAL = 0, 1, 2
 X_IMAGE, X_PRED, X_RAW0 = 0, 1, 2
 (OP_STEM, OP_CONV, OP_DW5, OP_MAXPOOL2, OP_SPP, OP_UPSAMPLE2, OP_CA, OP_ATTN_QK, OP_CRISSCROSS, OP_VERTICAL,
@@ -35,7 +35,7 @@ class OpDesc(C.Structure):
 
 EXPORTS = ['ry_abi_version', 'ry_abi_sizeof', 'ry_last_error', 'ry_plan_create', 'ry_plan_destroy', 'ry_plan_workspace_bytes',
            'ry_plan_bind', 'ry_plan_tensor_info', 'ry_plan_num_candidates', 'ry_plan_launch_count', 'ry_forward',
-           'ry_run_ops', 'ry_plan_set_profiling', 'ry_plan_op_times', 'ry_nms_workspace_bytes', 'ry_nms']
+           'ry_run_ops', 'ry_plan_set_image_dtype', 'ry_plan_set_profiling', 'ry_plan_op_times', 'ry_nms_workspace_bytes', 'ry_nms']
 
 _lib = None
 
@@ -66,6 +66,7 @@ def lib():
     L.ry_plan_launch_count.argtypes = [vp, C.POINTER(i32)]
     L.ry_forward.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     L.ry_run_ops.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp, vp]
+    L.ry_plan_set_image_dtype.argtypes = [vp, i32]
     L.ry_plan_set_profiling.argtypes = [vp, i32]
     L.ry_plan_op_times.argtypes = [vp, C.POINTER(C.c_float), i32]
     L.ry_nms_workspace_bytes.argtypes = [i32, i32, i32, i32, C.POINTER(sz)]

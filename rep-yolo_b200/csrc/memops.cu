@@ -41,15 +41,19 @@ __device__ __forceinline__ void cp_async4(uint32_t dst, const float *src, bool o
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(ok ? 4 : 0) : "memory");   // !ok: zero fill
 }
 
-template <int COUT>
-__global__ void __launch_bounds__(256) stem_kernel(const float *__restrict__ img, const float *__restrict__ w,
+// U8 = true: the image is uint8 NCHW (0..255) as the reference's detect.py ships it to the device (detect.py:73-78); the
+// /255 of detect.py:76 is fused here.  The patch is then fetched as 34 aligned 4-byte words per line.
+template <int COUT, bool U8>
+__global__ void __launch_bounds__(256) stem_kernel(const void *__restrict__ img_v, const float *__restrict__ w,
                                                    const float *__restrict__ bias, __nv_bfloat16 *__restrict__ out,
                                                    int B, int H, int W, int out_cs, int out_off) {
     pdl_trigger();
     constexpr int NT = COUT / 8;
+    constexpr int kElem = U8 ? 1 : 4;                                          // bytes per patch element
+    constexpr int kX0 = U8 ? 3 : 0;                                            // patch column 0 sits at this element offset
     extern __shared__ __align__(16) uint8_t stem_smem[];
-    float *patch = reinterpret_cast<float *>(stem_smem);                       // 2 x [lines][pitch] fp32, filled by cp.async
-    __nv_bfloat16 *stage = reinterpret_cast<__nv_bfloat16 *>(patch + 2 * kStemPatchFloats);   // [2 rows][64 px][COUT]
+    uint8_t *patch = stem_smem;                                                // 2 x [lines][pitch] elements, filled by cp.async
+    __nv_bfloat16 *stage = reinterpret_cast<__nv_bfloat16 *>(stem_smem + 2 * kStemPatchFloats * kElem);   // [2 rows][64 px][COUT]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
     const int Ho = H / 2, Wo = W / 2;
     // ---- per-thread constants: patch offsets of this thread's 8 K indices, weight fragments, bias ----
@@ -62,7 +66,7 @@ __global__ void __launch_bounds__(256) stem_kernel(const float *__restrict__ img
             const int k = s * 16 + 2 * t4 + (j & 1) + (j >> 1) * 8;
             kval[s * 4 + j] = k < 27;
             const int ci = k / 9, kh = (k % 9) / 3, kw = k % 3;
-            koff[s * 4 + j] = k < 27 ? (ci * (2 * kStemTH + 1) + kh) * kStemPitch + kw : 0;
+            koff[s * 4 + j] = k < 27 ? (ci * (2 * kStemTH + 1) + kh) * kStemPitch + kw + kX0 : 0;
         }
     uint32_t bw[NT][2][2];
 #pragma unroll
@@ -89,13 +93,24 @@ __global__ void __launch_bounds__(256) stem_kernel(const float *__restrict__ img
         for (int r = warp; r < kStemLines; r += 8) {   // one warp per (channel, input row) line
             const int ci = r / (2 * kStemTH + 1), yy = hi0 + r - ci * (2 * kStemTH + 1);
             const bool row_ok = yy >= 0 && yy < H;
-            const float *src = img + (((size_t)b * 3 + ci) * H + (row_ok ? yy : 0)) * W;
-            const uint32_t dst = patch_u + (uint32_t)(buf * kStemPatchFloats + r * kStemPitch) * 4;
+            const size_t row_base = (((size_t)b * 3 + ci) * H + (row_ok ? yy : 0)) * W;
+            const uint32_t dst = patch_u + (uint32_t)(buf * kStemPatchFloats + r * kStemPitch) * kElem;
+            if (U8) {
+                const uint8_t *src = static_cast<const uint8_t *>(img_v) + row_base;
 #pragma unroll
-            for (int j = 0; j < 5; ++j) {
-                const int x = lane + 32 * j, xx = wi0 + x;
-                const bool ok = row_ok && xx >= 0 && xx < W;
-                if (x < kStemPW) cp_async4(dst + x * 4, src + (ok ? xx : 0), ok);
+                for (int j = 0; j < 2; ++j) {
+                    const int wd = lane + 32 * j, xx = wi0 - 3 + 4 * wd;       // aligned 4-byte word: columns xx .. xx+3
+                    const bool ok = row_ok && xx >= 0 && xx < W;
+                    if (wd < 34) cp_async4(dst + wd * 4, reinterpret_cast<const float *>(src + (ok ? xx : 0)), ok);
+                }
+            } else {
+                const float *src = static_cast<const float *>(img_v) + row_base;
+#pragma unroll
+                for (int j = 0; j < 5; ++j) {
+                    const int x = lane + 32 * j, xx = wi0 + x;
+                    const bool ok = row_ok && xx >= 0 && xx < W;
+                    if (x < kStemPW) cp_async4(dst + x * 4, src + (ok ? xx : 0), ok);
+                }
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
@@ -114,11 +129,11 @@ __global__ void __launch_bounds__(256) stem_kernel(const float *__restrict__ img
             asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
         __syncthreads();
-        const float *pb = patch + buf * kStemPatchFloats;
+        const uint8_t *pb = patch + (size_t)buf * kStemPatchFloats * kElem;
         for (int rp = 0; rp < kStemTH / 2; ++rp) {
             // ---- warp = 16 consecutive pixels of one row of this row pair ----
             const int trow = warp / 4, px0 = (warp % 4) * 16;
-            const float *pp = pb + (2 * (2 * rp + trow)) * kStemPitch + 2 * px0;
+            const int base = (2 * (2 * rp + trow)) * kStemPitch + 2 * px0;
             uint32_t a[2][4];
 #pragma unroll
             for (int s = 0; s < 2; ++s)
@@ -126,9 +141,16 @@ __global__ void __launch_bounds__(256) stem_kernel(const float *__restrict__ img
                 for (int h = 0; h < 2; ++h) {               // h: k pair (2t,2t+1) / (2t+8,2t+9)
 #pragma unroll
                     for (int r = 0; r < 2; ++r) {           // r: pixel g / g+8
-                        const int pix = 2 * (g + 8 * r);
-                        const float lo = kval[s * 4 + 2 * h] ? pp[koff[s * 4 + 2 * h] + pix] : 0.0f;
-                        const float hi = kval[s * 4 + 2 * h + 1] ? pp[koff[s * 4 + 2 * h + 1] + pix] : 0.0f;
+                        const int pix = base + 2 * (g + 8 * r);
+                        float lo = 0.0f, hi = 0.0f;
+                        if (U8) {
+                            if (kval[s * 4 + 2 * h]) lo = (float)pb[koff[s * 4 + 2 * h] + pix] * (1.0f / 255.0f);
+                            if (kval[s * 4 + 2 * h + 1]) hi = (float)pb[koff[s * 4 + 2 * h + 1] + pix] * (1.0f / 255.0f);
+                        } else {
+                            const float *pf = reinterpret_cast<const float *>(pb);
+                            if (kval[s * 4 + 2 * h]) lo = pf[koff[s * 4 + 2 * h] + pix];
+                            if (kval[s * 4 + 2 * h + 1]) hi = pf[koff[s * 4 + 2 * h + 1] + pix];
+                        }
                         a[s][h * 2 + r] = pack_bf16x2(lo, hi);   // a0:(g,k lo) a1:(g+8,k lo) a2:(g,k hi) a3:(g+8,k hi)
                     }
                 }
@@ -411,29 +433,32 @@ inline int grid_for(size_t total, int block) {
 
 }  // namespace
 
-template <int COUT>
-void stem_launch_t(const float *img, const float *w27, const float *bias, __nv_bfloat16 *out, int out_cs, int out_off, int B, int H,
+template <int COUT, bool U8>
+void stem_launch_t(const void *img, const float *w27, const float *bias, __nv_bfloat16 *out, int out_cs, int out_off, int B, int H,
                    int W, cudaStream_t st) {
     const long tiles = (long)B * cdiv(H / 2, kStemTH) * cdiv(W / 2, kStemTW);
-    const size_t smem = (size_t)2 * kStemPatchFloats * 4 + (size_t)2 * kStemTW * COUT * 2;
+    const size_t smem = (size_t)2 * kStemPatchFloats * (U8 ? 1 : 4) + (size_t)2 * kStemTW * COUT * 2;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(stem_kernel<COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        cudaFuncSetAttribute(stem_kernel<COUT, U8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
         attr_set = true;
     }
     const int grid = (int)std::min<long>(tiles, (long)kNumSMs * 2);
-    launch_pdl(stem_kernel<COUT>, dim3(grid), dim3(256), smem, st, img, w27, bias, out, B, H, W, out_cs, out_off);
+    launch_pdl(stem_kernel<COUT, U8>, dim3(grid), dim3(256), smem, st, img, w27, bias, out, B, H, W, out_cs, out_off);
 }
 
-int stem_launch(const float *img, const float *w27, const float *bias, __nv_bfloat16 *out, int out_cs, int out_off,
+int stem_launch(const void *img, int img_u8, const float *w27, const float *bias, __nv_bfloat16 *out, int out_cs, int out_off,
                 int cout, int B, int H, int W, cudaStream_t st) {
+#define RY_STEM_CASE(C)                                                                                   \
+    case C:                                                                                               \
+        if (img_u8) stem_launch_t<C, true>(img, w27, bias, out, out_cs, out_off, B, H, W, st);            \
+        else stem_launch_t<C, false>(img, w27, bias, out, out_cs, out_off, B, H, W, st);                  \
+        break;
     switch (cout) {
-        case 16: stem_launch_t<16>(img, w27, bias, out, out_cs, out_off, B, H, W, st); break;
-        case 32: stem_launch_t<32>(img, w27, bias, out, out_cs, out_off, B, H, W, st); break;
-        case 48: stem_launch_t<48>(img, w27, bias, out, out_cs, out_off, B, H, W, st); break;
-        case 64: stem_launch_t<64>(img, w27, bias, out, out_cs, out_off, B, H, W, st); break;
+        RY_STEM_CASE(16) RY_STEM_CASE(32) RY_STEM_CASE(48) RY_STEM_CASE(64)
         default: return 1;
     }
+#undef RY_STEM_CASE
     return 0;
 }
 

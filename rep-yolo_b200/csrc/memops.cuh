@@ -5,7 +5,7 @@
 
 namespace ry {
 
-int stem_launch(const float *img, const float *w27, const float *bias, __nv_bfloat16 *out, int out_cs, int out_off,
+int stem_launch(const void *img, int img_u8, const float *w27, const float *bias, __nv_bfloat16 *out, int out_cs, int out_off,
                 int cout, int B, int H, int W, cudaStream_t st);
 void dw5_launch(const __nv_bfloat16 *in, int in_cs, int in_off0, int in_off1, __nv_bfloat16 *out, int out_cs, int out_off0,
                 int out_off1, const float *w, const float *bias, int C, int half, int B, int H, int W, int act,

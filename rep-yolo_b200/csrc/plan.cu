@@ -89,6 +89,7 @@ struct ry_plan {
     size_t tmaps_cap = 0;
     int n_cand = 0;
     // optional per-op CUDA-event timing (bench.py roofline): events[2*i], events[2*i+1] bracket op i
+    int image_u8 = 0;            // ry_plan_set_image_dtype: the `image` pointer is uint8 NCHW (0..255), /255 fused in the stem
     bool profiling = false;
     std::vector<cudaEvent_t> events;
 };
@@ -544,7 +545,7 @@ int run_op(ry_plan *p, Op &op, const float *image, float *pred, float *raws[3], 
         case RY_OP_STEM: {
             if (!image) RY_FAIL("stem: image pointer is NULL");
             const Tensor &to = p->tensors[d.out0.tensor];
-            if (stem_launch(image, wf(p, op.dev[0]), wf(p, op.dev[1]), bf(p, d.out0.tensor), to.d.channels, d.out0.c_off, d.cout, B,
+            if (stem_launch(image, p->image_u8, wf(p, op.dev[0]), wf(p, op.dev[1]), bf(p, d.out0.tensor), to.d.channels, d.out0.c_off, d.cout, B,
                             p->H, p->W, st))
                 RY_FAIL("stem: unsupported cout");
             break;
@@ -865,6 +866,12 @@ int ry_run_ops(ry_plan *p, int first, int last, const float *image, float *pred,
         if (p->profiling) cudaEventRecord(p->events[2 * i + 1], st);
     }
     RY_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int ry_plan_set_image_dtype(ry_plan *p, int dtype) {
+    if (!p || (dtype != RY_F32 && dtype != RY_U8)) RY_FAIL("set_image_dtype: RY_F32 or RY_U8");
+    p->image_u8 = dtype == RY_U8 ? 1 : 0;
     return 0;
 }
 

@@ -63,6 +63,7 @@ class NativeEngine:
         self.shape = None
         self.workspace = None
         self.n_cand = 0
+        self._image_u8 = False
 
     def __del__(self):
         try:
@@ -125,9 +126,16 @@ class NativeEngine:
         raws = [torch.empty((B, 3, H >> l, W >> l, no), dtype=torch.float32, device=self.device) for l in (3, 4, 5)]
         return pred, raws
 
+    def _set_image_dtype(self, x):
+        u8 = x.dtype == torch.uint8
+        if u8 != self._image_u8:
+            N.check(N.lib().ry_plan_set_image_dtype(self.handle, N.RY_U8 if u8 else N.RY_F32), 'ry_plan_set_image_dtype')
+            self._image_u8 = u8
+
     def forward(self, x):
         B, _, H, W = x.shape
         self.bind(B, H, W)
+        self._set_image_dtype(x)
         pred, raws = self._outputs(B, H, W)
         with torch.cuda.device(self.device):
             st = torch.cuda.current_stream(self.device).cuda_stream
@@ -137,6 +145,8 @@ class NativeEngine:
 
     def run_ops(self, first, last, image=None, pred=None, raws=(None, None, None)):
         ptr = lambda t: t.data_ptr() if t is not None else None
+        if image is not None:
+            self._set_image_dtype(image)
         with torch.cuda.device(self.device):
             st = torch.cuda.current_stream(self.device).cuda_stream
             N.check(N.lib().ry_run_ops(self.handle, first, last, ptr(image), ptr(pred), ptr(raws[0]), ptr(raws[1]), ptr(raws[2]),
@@ -225,7 +235,9 @@ class Model(nn.Module):
             raise RuntimeError('only the deployed path is built: call .fuse() first (attempt_load does)')
         if not x.is_cuda:
             raise N.NativeError('Model.forward: input must be a CUDA tensor (no CPU fallback on this path)')
-        if x.dtype != torch.float32 or not x.is_contiguous():
+        if x.dtype == torch.uint8:
+            x = x.contiguous()      # uint8 NCHW 0..255 (what detect.py:73 sends to the device): the /255 is fused in the stem
+        elif x.dtype != torch.float32 or not x.is_contiguous():
             x = x.float().contiguous()
         return self.engine(x.device).forward(x)
 

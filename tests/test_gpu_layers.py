@@ -178,3 +178,19 @@ def test_default_init_teacher_forced_1280_der_block():
     got = arena_to_nchw(eng, g.output)
     ref = O.run_fused_layer(fz, layers[1], x_in.bfloat16().float())
     assert rel_l2(got, ref) <= 3e-2
+
+
+def test_uint8_image_input_matches_float_input():
+    """uint8 NCHW input (what detect.py:73 ships to the device) with the /255 fused in the stem == float input / 255."""
+    import repyolo_b200 as R
+    layers, save, sd, fz = O.make_model(seed=0, mode='default')
+    m = R.Model()
+    m.load_state_dict(sd, strict=True)
+    m.fuse()
+    xb = torch.randint(0, 256, (2, 3, 128, 128), dtype=torch.uint8, generator=torch.Generator().manual_seed(4)).cuda()
+    p8, _ = m(xb)
+    pf, _ = m(xb.float() / 255.0)
+    p8b, _ = m(xb)                                   # switching back and forth keeps working
+    assert torch.equal(p8, p8b)
+    d = (p8 - pf).abs()
+    assert float(d[..., :4].max()) <= 0.05 and float(d[..., 4:].max()) <= 2e-3, (float(d[..., :4].max()), float(d[..., 4:].max()))
