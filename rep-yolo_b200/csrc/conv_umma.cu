@@ -253,8 +253,9 @@ __device__ __forceinline__ void epilogue_store_role(const ConvArgs &p, const Epi
         if (EXTRA) {                                          // pixel coordinates: residual / broadcast add only
             const int w = tc.w0 + w_in, h = tc.h0 + h_in, n = tc.n0 + n_in;
             valid = (n_in < p.tn) && (w < p.Wo) && (h < p.Ho) && (n < p.Bo);
-            pix = ((size_t)n * p.Ho + h) * p.Wo + w;
-            img = (int)(pix / p.img_hw);
+            const uint32_t pix32 = ((uint32_t)n * (uint32_t)p.Ho + (uint32_t)h) * (uint32_t)p.Wo + (uint32_t)w;   // < 2^31 pixels per batch
+            pix = pix32;
+            img = (int)(((uint64_t)pix32 * p.div_hw) >> 40);
         }
         ptx::mbar_wait(cx.tfull + acc, aph);
         ptx::tc_fence_after();

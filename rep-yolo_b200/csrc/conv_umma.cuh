@@ -57,6 +57,7 @@ struct ConvArgs {
     int16_t kb_coord[kConvMaxSrcBlocks];
     int tw, th, tn;            // output tile extent in w, h, image
     int tiles_w, tiles_h, tiles_n;
+    uint64_t div_hw;           // ceil(2^40 / img_hw): image index of a pixel = (pix * div_hw) >> 40
     uint32_t div_nt, div_tw, div_th;   // ceil(2^32 / d) for d = n_ntiles, tiles_w, tiles_h (0 when d == 1): exact q = umulhi(n, m)
     int n_ntiles, BN;          // output-channel tiling
     int Wo, Ho, Bo;            // logical output extent the tile grid covers (1x1: Wo = B*H*W, Ho = Bo = 1)

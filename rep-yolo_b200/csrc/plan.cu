@@ -328,7 +328,9 @@ int bind_conv(ry_plan *p, Op &op, std::vector<CUtensorMap> &maps) {
             }
         }
         a.tap_map[0] = 0; a.tap_dh[0] = 0; a.tap_dw[0] = 0;
-    } else if (s == 1 && !no_halo && Wo % kHaloTw == 0 && Ho % kHaloTh == 0) {
+    } else if (s == 1 && !no_halo && Wo % kHaloTw == 0 &&
+               (Ho % kHaloTh == 0 || (d.cout <= 128 && Ho * 5 >= cdiv(Ho, kHaloTh) * kHaloTh * 4))) {
+        // (partial last tile row: worth it for the small-N layers that are bound by L2 re-reads, not by the tensor pipe)
         // halo mode: one (8+2) x (16+2) pixel box per K block, the nine taps are descriptor windows into it
         a.a_mode = A_HALO;
         a.tw = kHaloTw; a.th = kHaloTh; a.tn = 1;
@@ -373,6 +375,7 @@ int bind_conv(ry_plan *p, Op &op, std::vector<CUtensorMap> &maps) {
     if (acc_env && atoi(acc_env) == 4 && 4 * cp.BN <= 512) a.n_acc = 4;
     if (acc_env && atoi(acc_env) == 2) a.n_acc = 2;
     a.tiles_w = cdiv(a.Wo, a.tw); a.tiles_h = cdiv(a.Ho, a.th); a.tiles_n = cdiv(a.Bo, a.tn);
+    a.div_hw = (uint64_t)(((1ull << 40) + (uint64_t)a.img_hw - 1) / (uint64_t)a.img_hw);
     {
         auto magic = [](int d) -> uint32_t { return d <= 1 ? 0u : (uint32_t)(((1ull << 32) + (uint64_t)d - 1) / (uint64_t)d); };
         a.div_nt = magic(a.n_ntiles); a.div_tw = magic(a.tiles_w); a.div_th = magic(a.tiles_h);
