@@ -46,15 +46,25 @@ class ClockSampler(threading.Thread):
     def run(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
-                                          '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          '-lms', '50'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
                 self.rows.append([c.strip() for c in line.split(',')])
         except Exception:
             pass
 
-    def stop(self):
+    def wait_first(self, timeout=5.0):
+        """nvidia-smi needs ~0.3-1 s to deliver its first row: block until it has, so a short timed region is covered"""
+        t0 = time.perf_counter()
+        while not self.rows and time.perf_counter() - t0 < timeout:
+            time.sleep(0.02)
+
+    def mark(self):
+        return len(self.rows)
+
+    def stop(self, first=0):
         if self.proc:
             self.proc.terminate()
+        self.rows = self.rows[first:]
         sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
         mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
         reasons = set()
@@ -158,11 +168,16 @@ def run_native(args):
             torch.cuda.synchronize(dev)
 
     # ---- kernel-resident throughput (inputs already in HBM) ----
+    sampler = ClockSampler(local)
+    sampler.start()
     for i in range(args.warmup):
         step(xdev[i % n_bufs])
     sync_all()
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler.wait_first()
+    for i in range(args.warmup):                      # GPU busy again right before the timed region (the wait above idled it)
+        step(xdev[i % n_bufs])
+    sync_all()
+    mark = sampler.mark()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
@@ -170,7 +185,6 @@ def run_native(args):
     e1.record()
     sync_all()
     ms = e0.elapsed_time(e1)
-    clocks = sampler.stop()
 
     # ---- end to end through the public API: pinned host batch -> H2D -> forward -> NMS -> D2H of the detections ----
     copy_stream = torch.cuda.Stream(dev)
@@ -210,6 +224,7 @@ def run_native(args):
     t1.record()
     sync_all()
     ms_e2e = t0.elapsed_time(t1)
+    clocks = sampler.stop(mark)                        # samples taken from the start of the first timed region to the end of the second
 
     # ---- roofline of the dominant kernel (conv_umma_kernel): per-op CUDA events over K more steps ----
     ops = eng.plan_ir.ops
@@ -310,7 +325,7 @@ def run_native(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=50)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='native', choices=['native', 'reference'])
     ap.add_argument('--batch', type=int, default=64)

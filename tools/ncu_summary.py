@@ -14,6 +14,7 @@ KEYS = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'l1tex__m_xbar2l1tex_read_bytes.sum', 'lts__t_bytes.sum', 'lts__t_sector_hit_rate.pct',
         'sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed',
         'sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg', 'sm__throughput.avg.pct_of_peak_sustained_elapsed',
+        'l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed', 'sm__inst_executed_pipe_tc.sum', 'sm__inst_executed_pipe_tma.sum',
         'sm__warps_active.avg.pct_of_peak_sustained_active', 'launch__registers_per_thread', 'launch__grid_size', 'launch__block_size',
         'launch__shared_mem_per_block_dynamic', 'smsp__cycles_active.avg', 'sm__cycles_elapsed.avg', 'sm__cycles_elapsed.avg.per_second']
 
