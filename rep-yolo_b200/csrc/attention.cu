@@ -7,7 +7,8 @@
 //                Two "line attention" passes merged like a split soft-max:
 //                  row pass  (CTA = one image row)    -> un-normalised partial O_W, running max m_W, sum s_W (scratch)
 //                  col pass  (CTA = one image column) -> O_H, m_H, s_H, merge with the row partials, gamma*out + x
-//  vertical    : out[y=j,x=i] = sum_k v[k,i] * (q[i,j].k[k,j])   (raw energies, H == W; common.py:3763-3778)
+//  vertical    : out[y=i,x=n] = sum_j v[j,n] * E(m = n*H + i)[j],  E(h*W + w)[j] = q[h,w].k[j,w]   (raw energies; the flat
+//                re-view of the reference mixes rows and columns, common.py:3763-3778; H == W: out[y,x] = sum_j v[j,x] q[x,y].k[j,y])
 //                  energy pass (CTA = image column j): E_j[i][k] = q[i,j].k[k,j]  -> bf16 scratch [b][i][j][k]
 //                  value pass  (CTA = output column i): out[j,i] = E[i][j][:] . v[:,i]; gamma*out + x
 //  v = ReLU6(bn1(SiLU(wv*x + bv))) is recomputed from x where needed (depthwise 1x1: purely per element).
@@ -155,7 +156,9 @@ __global__ void __launch_bounds__(NT * 16 * LPC) attn_mma_kernel(const AttnParam
     }
     if (MODE == MODE_VPV && active) {
         // P[j][k] = E[b][i = line][j][k] (bf16 scratch written by the energy pass), rows j >= L are zero
-        const __nv_bfloat16 *E = reinterpret_cast<const __nv_bfloat16 *>(p.scratch) + ((size_t)b * p.H + line) * p.W * LP;
+        // general H x W (the reference's view chain, common.py:3763-3775): output column n' uses the H energy rows of the
+        // flat pixels n'*H .. n'*H + H-1 (row-major) -- for H == W that is image row n'
+        const __nv_bfloat16 *E = reinterpret_cast<const __nv_bfloat16 *>(p.scratch) + ((size_t)b * p.H * p.W + (size_t)line * p.H) * LP;
         const int vecs = LP / 8;
         for (int idx = tis; idx < LP * vecs; idx += kThreads) {
             const int j = idx / vecs, c = (idx - j * vecs) * 8;
@@ -364,7 +367,6 @@ int crisscross_launch(const AttnParams &p, cudaStream_t st) {
 }
 
 int vertical_launch(const AttnParams &p, cudaStream_t st) {
-    if (p.H != p.W) return 2;   // the reference's view chain scrambles indices for H != W: not built yet
     if (launch_mode<MODE_VE>(p, st)) return 1;
     return launch_mode<MODE_VPV>(p, st);
 }

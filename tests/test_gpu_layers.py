@@ -20,7 +20,7 @@ TOL = {'RepS_Block': 8e-3, 'DER_Block': 3e-2, 'MP': 2e-3, 'SPPCSPC': 3e-2, 'GSCo
        'VoVGSCSP': 3e-2, 'Conv': 8e-3, 'CA': 6e-3, 'CCVA': 3e-2, 'RepConv': 8e-3}
 
 
-@pytest.fixture(scope='module', params=[(2, 128), (1, 640)], ids=['b2x128', 'b1x640'])
+@pytest.fixture(scope='module', params=[(2, 128), (1, 640), (1, (96, 160))], ids=['b2x128', 'b1x640', 'b1x96x160'])
 def bound(request, oracle_model):
     import repyolo_b200 as R
     B, size = request.param
@@ -28,10 +28,11 @@ def bound(request, oracle_model):
     m = R.Model()
     m.load_state_dict(sd, strict=True)
     m.fuse()
-    x0 = torch.rand(B, 3, size, size, generator=torch.Generator().manual_seed(100 + size))
+    H, W = (size, size) if isinstance(size, int) else size          # non-square: letterboxed detect.py inputs, VerticalAttention's view chain
+    x0 = torch.rand(B, 3, H, W, generator=torch.Generator().manual_seed(100 + H))
     outs, pred, raws = O.forward_fused(fz, layers, save, x0)
     eng = m.engine('cuda:0')
-    eng.bind(B, size, size)
+    eng.bind(B, H, W)
     return dict(m=m, eng=eng, x0=x0, outs=outs, layers=layers, fz=fz, B=B, size=size)
 
 
@@ -74,7 +75,8 @@ def test_detect_decode_teacher_forced(bound):
     feats = [o / o.pow(2).mean().sqrt() for o in (outs[62], outs[63], outs[64])]
     for (src, view), f in zip(g.inputs, feats):
         nchw_to_arena(eng, view, f)
-    pred, raws = eng._outputs(B, size, size)
+    H, W = (size, size) if isinstance(size, int) else size
+    pred, raws = eng._outputs(B, H, W)
     eng.run_ops(g.first_op, g.last_op, pred=pred, raws=raws)
     torch.cuda.synchronize()
     p = pred.cpu()
