@@ -218,6 +218,7 @@ class Model(nn.Module):
         self.stride = self.model[-1].stride
         self._fused = None
         self._engine = None
+        self._engines = {}
 
     # ---- reference API ----
     def fuse(self):
@@ -226,11 +227,12 @@ class Model(nn.Module):
             with torch.no_grad():
                 self._fused = fold.fold_state_dict(self.state_dict(), self._layers)
             self._engine = None
+            self._engines = {}
         return self
 
     def forward(self, x, augment=False, profile=False):
         if augment:
-            raise NotImplementedError('test-time augmentation (models/yolo.py:570-585) is not built yet')
+            return self._forward_augment(x)
         if self._fused is None:
             raise RuntimeError('only the deployed path is built: call .fuse() first (attempt_load does)')
         if not x.is_cuda:
@@ -239,17 +241,57 @@ class Model(nn.Module):
             x = x.contiguous()      # uint8 NCHW 0..255 (what detect.py:73 sends to the device): the /255 is fused in the stem
         elif x.dtype != torch.float32 or not x.is_contiguous():
             x = x.float().contiguous()
-        return self.engine(x.device).forward(x)
+        return self.engine(x.device, (x.shape[0], x.shape[2], x.shape[3])).forward(x)
+
+    def _forward_augment(self, x):
+        """Test-time augmentation exactly as the reference (models/yolo.py:570-585, utils/torch_utils.py:247-257): scales
+        1 / 0.83 / 0.67 (bilinear, padded with 0.447 to a multiple of the max stride), the middle one left-right flipped;
+        boxes de-scaled / de-flipped, predictions concatenated.  The resize / flip of the INPUT is host-side torch plumbing;
+        every forward runs in the native engine (one cached engine per shape)."""
+        import torch.nn.functional as F
+        if x.dtype == torch.uint8:
+            x = x.float() / 255.0
+        img_size = x.shape[-2:]
+        gs = int(self.stride.max())
+        y = []
+        for si, fi in zip((1, 0.83, 0.67), (None, 3, None)):
+            xi = x.flip(fi) if fi else x
+            if si != 1:
+                h, w = xi.shape[2:]
+                s = (int(h * si), int(w * si))
+                xi = F.interpolate(xi, size=s, mode='bilinear', align_corners=False)
+                h, w = [math.ceil(v * si / gs) * gs for v in (h, w)]
+                xi = F.pad(xi, [0, w - s[1], 0, h - s[0]], value=0.447)
+            yi = self.forward(xi.contiguous())[0]
+            yi[..., :4] /= si
+            if fi == 3:
+                yi[..., 0] = img_size[1] - yi[..., 0]
+            y.append(yi)
+        return torch.cat(y, 1), None
 
     def info(self, verbose=False, img_size=640):
         n_p = sum(p.numel() for p in self.parameters())
         print(f'Model Summary: {len(self._layers)} layers, {n_p} parameters (native B200 deploy path)')
 
     # ---- native plumbing ----
-    def engine(self, device):
-        if self._engine is None or self._engine.device != torch.device(device):
-            self._engine = NativeEngine(planner.lower(self._layers, self._fused, self.yaml['nc']), self.yaml['nc'], device)
-        return self._engine
+    def engine(self, device, shape=None):
+        """The engine for `device`; with `shape` = (B, H, W) one engine per shape is cached (TTA / alternating shapes would
+        otherwise re-bind arena and tensor maps on every call)."""
+        device = torch.device(device)
+        if self._engine is not None and self._engine.device == device and (shape is None or self._engine.shape in (None, shape)):
+            return self._engine
+        key = (device, shape)
+        eng = self._engines.get(key) if shape is not None else None
+        if eng is None:
+            eng = NativeEngine(planner.lower(self._layers, self._fused, self.yaml['nc']), self.yaml['nc'], device)
+            if shape is not None:
+                if self._engine is not None and self._engine.shape is not None:
+                    self._engines[(self._engine.device, self._engine.shape)] = self._engine
+                while len(self._engines) >= 4:
+                    self._engines.pop(next(iter(self._engines)))
+                self._engines[key] = eng
+        self._engine = eng
+        return eng
 
     def _detect_only(self, xs):
         eng = self.engine(xs[0].device)

@@ -196,3 +196,37 @@ def test_uint8_image_input_matches_float_input():
     assert torch.equal(p8, p8b)
     d = (p8 - pf).abs()
     assert float(d[..., :4].max()) <= 0.05 and float(d[..., 4:].max()) <= 2e-3, (float(d[..., :4].max()), float(d[..., 4:].max()))
+
+
+def test_tta_augment_matches_reference_recipe():
+    """Model.forward(augment=True) (models/yolo.py:570-585): three scales, middle one flipped, de-scaled and concatenated.
+    Checked against the same recipe driven through the CPU oracle (default init: near-linear regime)."""
+    import math
+    import torch.nn.functional as F
+    import repyolo_b200 as R
+    layers, save, sd, fz = O.make_model(seed=0, mode='default')
+    m = R.Model()
+    m.load_state_dict(sd, strict=True)
+    m.fuse()
+    x = torch.rand(1, 3, 192, 192, generator=torch.Generator().manual_seed(9))
+    pred, none = m(x.cuda(), augment=True)
+    assert none is None
+    ys = []
+    for si, fi in zip((1, 0.83, 0.67), (None, 3, None)):
+        xi = x.flip(fi) if fi else x
+        if si != 1:
+            s = (int(192 * si), int(192 * si))
+            xi = F.interpolate(xi, size=s, mode='bilinear', align_corners=False)
+            hw = math.ceil(192 * si / 32) * 32
+            xi = F.pad(xi, [0, hw - s[1], 0, hw - s[0]], value=0.447)
+        yi = O.forward_fused(fz, layers, save, xi)[1]
+        yi[..., :4] /= si
+        if fi == 3:
+            yi[..., 0] = 192 - yi[..., 0]
+        ys.append(yi)
+    ref = torch.cat(ys, 1)
+    assert pred.shape == ref.shape
+    d = (pred.cpu() - ref).abs()
+    assert float(d[..., :4].max()) <= 0.15 and float(d[..., 4:].max()) <= 3.2e-3, (float(d[..., :4].max()), float(d[..., 4:].max()))
+    p2, _ = m(x.cuda())                               # plain forward still works after the shape changes
+    assert torch.allclose(p2, pred[:, :p2.shape[1]], atol=0, rtol=0)
