@@ -10,3 +10,4 @@ from .nms import non_max_suppression, nms_padded          # noqa: F401
 from ._lib import NativeError, lib                        # noqa: F401
 from .arch import rep_yolo_cfg                            # noqa: F401
 from .parallel import gather_detections, shard_bounds, to_list  # noqa: F401
+from .compat import attempt_load, from_reference, TracedModel, Ensemble, install as install_into_reference  # noqa: F401

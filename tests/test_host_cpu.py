@@ -123,3 +123,49 @@ def test_product_does_not_import_oracle():
             if f.endswith(('.py', '.cu', '.cuh', '.h')):
                 src = open(os.path.join(dirpath, f)).read()
                 assert 'oracle' not in src, os.path.join(dirpath, f)
+
+
+def test_compat_install_patches_reference_modules():
+    """compat.install() rebinds attempt_load / TracedModel / non_max_suppression inside (stand-in) reference modules,
+    including the copies `from x import y` left in an already imported caller."""
+    import sys
+    import types
+    import repyolo_b200 as R
+    compat = importlib.import_module('rep-yolo_b200.compat')
+    fake = {}
+    for name in ('models', 'models.experimental', 'utils', 'utils.torch_utils', 'utils.general', 'detect'):
+        fake[name] = types.ModuleType(name)
+    def ref_fn(*a, **k):
+        raise AssertionError('reference implementation called')
+    for mod, attr in (('models.experimental', 'attempt_load'), ('utils.torch_utils', 'TracedModel'),
+                      ('utils.general', 'non_max_suppression'), ('detect', 'attempt_load'), ('detect', 'non_max_suppression')):
+        f = types.FunctionType(ref_fn.__code__, globals(), attr)
+        f.__module__ = 'models.experimental' if attr == 'attempt_load' else ('utils.torch_utils' if attr == 'TracedModel' else 'utils.general')
+        setattr(fake[mod], attr, f)
+    saved = {k: sys.modules.get(k) for k in fake}
+    sys.modules.update(fake)
+    try:
+        patched = compat.install()
+        assert ('detect', 'attempt_load') in patched and ('utils.general', 'non_max_suppression') in patched
+        assert fake['detect'].non_max_suppression is R.non_max_suppression
+        assert fake['utils.torch_utils'].TracedModel is compat.TracedModel
+        assert fake['models.experimental'].attempt_load is compat.attempt_load
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+
+
+def test_from_reference_accepts_reference_state_dict(oracle_model):
+    """from_reference() needs only .yaml / .state_dict() / .names of the reference Model (same parameter names)."""
+    import types
+    import repyolo_b200 as R
+    arch = importlib.import_module('rep-yolo_b200.arch')
+    _, _, sd, _ = oracle_model
+    ref = types.SimpleNamespace(yaml=arch.rep_yolo_cfg(), state_dict=lambda: sd, names=['person'])
+    m = R.from_reference(ref)
+    assert m.names == ['person'] and m.fuse() is m
+    t = R.TracedModel(m, 'cpu', 640)
+    assert t.model is m and t.detect_layer is m.model[-1]
