@@ -169,6 +169,20 @@ class IDetect(_Node):
         """x: list of nl NCHW feature maps.  Mutates the list in place like the reference (yolo.py:140-142)."""
         return self._owner._detect_only(x)
 
+    def _package(self, pred, raws):
+        """Output contracts of IDetect.fuseforward (models/yolo.py:158-166): export -> raw head maps, end2end -> pred only,
+        include_nms -> convert() (box xyxy via the 4x4 matrix, score = cls * obj; yolo.py:189-199), else (pred, raw list)."""
+        if self.export:
+            return raws
+        if self.end2end:
+            return pred
+        if self.include_nms:
+            box, conf, score = pred[:, :, :4], pred[:, :, 4:5], pred[:, :, 5:]
+            score = score * conf
+            m = torch.tensor([[1, 0, 1, 0], [0, 1, 0, 1], [-0.5, 0, 0.5, 0], [0, -0.5, 0, 0.5]], dtype=torch.float32, device=pred.device)
+            return ((box @ m, score),)
+        return (pred, raws)
+
     forward = fuseforward
 
 
@@ -241,7 +255,8 @@ class Model(nn.Module):
             x = x.contiguous()      # uint8 NCHW 0..255 (what detect.py:73 sends to the device): the /255 is fused in the stem
         elif x.dtype != torch.float32 or not x.is_contiguous():
             x = x.float().contiguous()
-        return self.engine(x.device, (x.shape[0], x.shape[2], x.shape[3])).forward(x)
+        pred, raws = self.engine(x.device, (x.shape[0], x.shape[2], x.shape[3])).forward(x)
+        return self.model[-1]._package(pred, raws)
 
     def _forward_augment(self, x):
         """Test-time augmentation exactly as the reference (models/yolo.py:570-585, utils/torch_utils.py:247-257): scales
@@ -262,7 +277,7 @@ class Model(nn.Module):
                 xi = F.interpolate(xi, size=s, mode='bilinear', align_corners=False)
                 h, w = [math.ceil(v * si / gs) * gs for v in (h, w)]
                 xi = F.pad(xi, [0, w - s[1], 0, h - s[0]], value=0.447)
-            yi = self.forward(xi.contiguous())[0]
+            yi = self.engine(xi.device, (xi.shape[0], xi.shape[2], xi.shape[3])).forward(xi.contiguous())[0]
             yi[..., :4] /= si
             if fi == 3:
                 yi[..., 0] = img_size[1] - yi[..., 0]
@@ -305,7 +320,4 @@ class Model(nn.Module):
         eng.run_ops(grp.first_op, grp.last_op, pred=pred, raws=raws)
         for i in range(len(xs)):
             xs[i] = raws[i]
-        det = self.model[-1]
-        if det.end2end:
-            return pred
-        return (pred, xs)
+        return self.model[-1]._package(pred, xs)

@@ -230,3 +230,25 @@ def test_tta_augment_matches_reference_recipe():
     assert float(d[..., :4].max()) <= 0.15 and float(d[..., 4:].max()) <= 3.2e-3, (float(d[..., :4].max()), float(d[..., 4:].max()))
     p2, _ = m(x.cuda())                               # plain forward still works after the shape changes
     assert torch.allclose(p2, pred[:, :p2.shape[1]], atol=0, rtol=0)
+
+
+def test_idetect_output_contracts():
+    """end2end / include_nms / export branches of IDetect.fuseforward (models/yolo.py:158-166, convert() :189-199)."""
+    import repyolo_b200 as R
+    layers, save, sd, fz = O.make_model(seed=0, mode='default')
+    m = R.Model()
+    m.load_state_dict(sd, strict=True)
+    m.fuse()
+    x = torch.rand(1, 3, 64, 64, generator=torch.Generator().manual_seed(2)).cuda()
+    pred, raws = m(x)
+    det = m.model[-1]
+    det.end2end = True
+    assert torch.equal(m(x), pred)
+    det.end2end, det.include_nms = False, True
+    (box, score), = m(x)
+    conv = torch.tensor([[1, 0, 1, 0], [0, 1, 0, 1], [-0.5, 0, 0.5, 0], [0, -0.5, 0, 0.5]], device=x.device)
+    assert torch.equal(box, pred[:, :, :4] @ conv) and torch.equal(score, pred[:, :, 5:] * pred[:, :, 4:5])
+    det.include_nms, det.export = False, True
+    out = m(x)
+    assert isinstance(out, list) and len(out) == 3 and torch.equal(out[0], raws[0])
+    det.export = False
