@@ -237,18 +237,19 @@ inline const float *wf(ry_plan *p, size_t off) { return reinterpret_cast<const f
 
 // Output channels of one N tile -> store segments (power-of-two widths, each with its own swizzled staging layout and TMA
 // store map), spread over the two epilogue column groups.
-struct OutPiece { int col0, len, chan; };
+struct OutPiece { int col0, len, chan, slot; };   // slot: 0 = out0's tensor, 1 = out1's tensor (split store into two tensors)
 
-void build_segments(ConvArgs &a, const OutPiece *pieces, int n_pieces, int max_cols, int widths[4], int *n_widths) {
+// widths[] holds one key per store map: slot * 1000 + box width
+void build_segments(ConvArgs &a, const OutPiece *pieces, int n_pieces, int max_cols, int widths[8], int *n_widths) {
     int total = 0;
     for (int i = 0; i < n_pieces; ++i) total += pieces[i].len;
-    struct S { int col0, ncol, chan; };
+    struct S { int col0, ncol, chan, slot; };
     std::vector<S> segs;
     // small N: one segment per output piece (dense rows unless the width is a power of two), the two epilogue groups work
     // as teams on alternate tiles; otherwise power-of-two segments spread over two column groups
     a.ep_teams = (total <= 64 && n_pieces <= kConvMaxSegs) ? 1 : 0;
     if (a.ep_teams) {
-        for (int i = 0; i < n_pieces; ++i) segs.push_back({pieces[i].col0, pieces[i].len, pieces[i].chan});
+        for (int i = 0; i < n_pieces; ++i) segs.push_back({pieces[i].col0, pieces[i].len, pieces[i].chan, pieces[i].slot});
     } else {
         int wmax = 8;
         while (wmax * 2 <= max_cols && wmax * 2 <= std::max(8, total / 2)) wmax *= 2;
@@ -256,7 +257,7 @@ void build_segments(ConvArgs &a, const OutPiece *pieces, int n_pieces, int max_c
             for (int c = 0; c < pieces[i].len;) {
                 int w = wmax;
                 while (w > pieces[i].len - c) w /= 2;
-                segs.push_back({pieces[i].col0 + c, w, pieces[i].chan + c});
+                segs.push_back({pieces[i].col0 + c, w, pieces[i].chan + c, pieces[i].slot});
                 c += w;
             }
         std::stable_sort(segs.begin(), segs.end(), [](const S &x, const S &y) { return x.ncol > y.ncol; });
@@ -266,8 +267,9 @@ void build_segments(ConvArgs &a, const OutPiece *pieces, int n_pieces, int max_c
     a.nseg[0] = a.nseg[1] = 0;
     for (const S &sg : segs) {
         int wi = 0;
-        while (wi < *n_widths && widths[wi] != sg.ncol) ++wi;
-        if (wi == *n_widths) widths[(*n_widths)++] = sg.ncol;
+        const int key = sg.slot * 1000 + sg.ncol;
+        while (wi < *n_widths && widths[wi] != key) ++wi;
+        if (wi == *n_widths) widths[(*n_widths)++] = key;
         for (int g = 0; g < 2; ++g) {
             if (!a.ep_teams && g != (load[1] < load[0] ? 1 : 0)) continue;
             ConvSeg &d = a.seg[g][a.nseg[g]++];
@@ -411,23 +413,25 @@ int bind_conv(ry_plan *p, Op &op, std::vector<CUtensorMap> &maps) {
     int n_pieces = 1;
     cuuint64_t c_end = (cuuint64_t)tout.d.channels;
     if (d.out1.tensor >= 0) {
-        if (d.out1.tensor != d.out0.tensor || cp.n_ntiles != 1 || d.out0.c_len + d.out1.c_len != d.cout) RY_FAIL("conv: bad split store");
-        pieces[0] = {0, d.out0.c_len, d.out0.c_off};
-        pieces[1] = {d.out0.c_len, d.out1.c_len, d.out1.c_off};
+        const Tensor &t1 = p->tensors[d.out1.tensor];
+        if (cp.n_ntiles != 1 || d.out0.c_len + d.out1.c_len != d.cout || t1.h != Ho || t1.w != Wo) RY_FAIL("conv: bad split store");
+        pieces[0] = {0, d.out0.c_len, d.out0.c_off, 0};
+        pieces[1] = {d.out0.c_len, d.out1.c_len, d.out1.c_off, 1};   // may be another tensor (two 1x1 convs of one input merged)
         n_pieces = 2;
     } else if (cp.n_ntiles == 1) {
-        pieces[0] = {0, d.cout, d.out0.c_off};
+        pieces[0] = {0, d.cout, d.out0.c_off, 0};
     } else {
-        pieces[0] = {0, cp.BN, d.out0.c_off};                       // per N tile; channels past the view are clipped by the map
+        pieces[0] = {0, cp.BN, d.out0.c_off, 0};                    // per N tile; channels past the view are clipped by the map
         c_end = (cuuint64_t)(d.out0.c_off + d.out0.c_len);
     }
-    int widths[4], n_widths = 0;
+    int widths[8], n_widths = 0;
     int max_cols = 64;
     build_segments(a, pieces, n_pieces, max_cols, widths, &n_widths);
-    if (conv_plan_smem(a, *std::max_element(widths, widths + n_widths))) RY_FAIL("conv: shared memory plan failed");
-    if (!a.ep_teams && !a.b_resident && a.a_mode == A_BOX && a.a_stages < 4 && widths[0] > 32) {   // big tiles: trade staging for pipeline depth
+    auto max_w = [&]() { int m = 8; for (int i = 0; i < n_widths; ++i) m = std::max(m, widths[i] % 1000); return m; };
+    if (conv_plan_smem(a, max_w())) RY_FAIL("conv: shared memory plan failed");
+    if (!a.ep_teams && !a.b_resident && a.a_mode == A_BOX && a.a_stages < 4 && max_w() > 32) {   // big tiles: trade staging for pipeline depth
         build_segments(a, pieces, n_pieces, 32, widths, &n_widths);
-        if (conv_plan_smem(a, *std::max_element(widths, widths + n_widths))) RY_FAIL("conv: shared memory plan failed");
+        if (conv_plan_smem(a, max_w())) RY_FAIL("conv: shared memory plan failed");
     }
     if (a.nseg[0] > kConvMaxSegs || a.nseg[1] > kConvMaxSegs) RY_FAIL("conv: too many store segments");
     {
@@ -437,18 +441,21 @@ int bind_conv(ry_plan *p, Op &op, std::vector<CUtensorMap> &maps) {
         if (a.n_groups == 4) a.n_acc = 4;
     }
     for (int wi = 0; wi < n_widths; ++wi) {
-        const cuuint64_t oc = (cuuint64_t)tout.d.channels;
+        const int slot = widths[wi] / 1000, wd = widths[wi] % 1000;
+        const int ot = slot ? d.out1.tensor : d.out0.tensor;
+        const cuuint64_t oc = (cuuint64_t)p->tensors[ot].d.channels;
+        const cuuint64_t ce = n_pieces == 2 ? oc : c_end;
         if (k == 1) {
             const cuuint64_t P = (cuuint64_t)a.Wo;
-            const cuuint64_t dims[4] = {c_end, P, 1, 1};
+            const cuuint64_t dims[4] = {ce, P, 1, 1};
             const cuuint64_t str[3] = {oc * esz, P * oc * esz, P * oc * esz};
-            const cuuint32_t box[4] = {(cuuint32_t)widths[wi], 128, 1, 1};
-            if (encode_map(&m, bf(p, d.out0.tensor), 4, dims, str, box, widths[wi])) return 1;
+            const cuuint32_t box[4] = {(cuuint32_t)wd, 128, 1, 1};
+            if (encode_map(&m, bf(p, ot), 4, dims, str, box, wd)) return 1;
         } else {
-            const cuuint64_t dims[4] = {c_end, (cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)B};
+            const cuuint64_t dims[4] = {ce, (cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)B};
             const cuuint64_t str[3] = {oc * esz, (cuuint64_t)Wo * oc * esz, (cuuint64_t)Ho * Wo * oc * esz};
-            const cuuint32_t box[4] = {(cuuint32_t)widths[wi], (cuuint32_t)a.tw, (cuuint32_t)a.th, (cuuint32_t)a.tn};
-            if (encode_map(&m, bf(p, d.out0.tensor), 4, dims, str, box, widths[wi])) return 1;
+            const cuuint32_t box[4] = {(cuuint32_t)wd, (cuuint32_t)a.tw, (cuuint32_t)a.th, (cuuint32_t)a.tn};
+            if (encode_map(&m, bf(p, ot), 4, dims, str, box, wd)) return 1;
         }
         maps.push_back(m);
     }

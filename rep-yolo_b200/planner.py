@@ -117,6 +117,19 @@ class Plan:
             prev = w.shape[0]
 
 
+    def conv_pair(self, layer, wb1, wb2, src, dst1, dst2, act=True):
+        """Two 1x1 convs of the same input (CCVA / VoVGSCSP / SPPCSPC cv1 + cv2) as ONE conv with a split store (the two halves may
+        go to different tensors): the input is read once, one launch instead of two."""
+        (w1, b1), (w2, b2) = wb1, wb2
+        if not merge_pairs or w1.shape[0] + w2.shape[0] > 256 or w1.shape[0] % 16:
+            self.conv(layer, w1, b1, src, dst1, act=act)
+            return self.conv(layer, w2, b2, src, dst2, act=act)
+        return self.conv(layer, torch.cat([w1, w2], 0), torch.cat([b1, b2], 0), src, dst1, act=act, dst2=dst2)
+
+
+merge_pairs = True
+
+
 def _gs_perm(c):
     return list(range(0, c, 2)) + list(range(1, c, 2))
 
@@ -238,14 +251,13 @@ def lower(layers, fz, nc=1, fuse_chains=None):
             c_, lvl = a[1], lvl_in
             ta, tb, tc = (P.full(P.tensor(c_, lvl)) for _ in range(3))
             cat4, cat2 = P.tensor(4 * c_, lvl), P.tensor(2 * c_, lvl)
-            P.conv(L.i, *W(f'{p}.cv1.conv'), x, ta)
+            P.conv_pair(L.i, W(f'{p}.cv1.conv'), W(f'{p}.cv2.conv'), x, ta, (cat2, c_, c_))
             P.conv(L.i, *W(f'{p}.cv3.conv'), ta, tb)
             P.conv(L.i, *W(f'{p}.cv4.conv'), tb, (cat4, 0, c_))
             P.op(N.OP_SPP, L.i, in0=(cat4, 0, c_), out0=(cat4, c_, c_), out1=(cat4, 2 * c_, c_), out2=(cat4, 3 * c_, c_),
                  cin=c_, cout=c_)
             P.conv(L.i, *W(f'{p}.cv5.conv'), P.full(cat4), tc)
             P.conv(L.i, *W(f'{p}.cv6.conv'), tc, (cat2, 0, c_))
-            P.conv(L.i, *W(f'{p}.cv2.conv'), x, (cat2, c_, c_))
             dst = out_view(L, lvl)
             P.conv(L.i, *W(f'{p}.cv7.conv'), P.full(cat2), dst)
         elif L.kind == 'GSConv':
@@ -261,8 +273,7 @@ def lower(layers, fz, nc=1, fuse_chains=None):
             c_, lvl = a[1] // 2, lvl_in
             cat = P.tensor(2 * c_, lvl)
             t, g0, g1 = (P.full(P.tensor(c_, lvl)) for _ in range(3))
-            P.conv(L.i, *W(f'{p}.cv2.conv'), x, (cat, 0, c_))
-            P.conv(L.i, *W(f'{p}.cv1.conv'), x, t)
+            P.conv_pair(L.i, W(f'{p}.cv1.conv'), W(f'{p}.cv2.conv'), x, t, (cat, 0, c_))
             gsconv(L.i, f'{p}.gsb.0.conv_lighting.0', t, g0, 1, 1, True, lvl)
             gsconv(L.i, f'{p}.gsb.0.conv_lighting.1', g0, g1, 3, 1, False, lvl)
             P.conv(L.i, *W(f'{p}.gsb.0.shortcut.conv'), t, (cat, c_, c_), act=False, res=g1)
@@ -290,10 +301,9 @@ def lower(layers, fz, nc=1, fuse_chains=None):
             cat = P.tensor(2 * c_, lvl)
             ta, tb = P.full(P.tensor(c_, lvl)), P.full(P.tensor(c_, lvl))
             q, k = P.full(P.tensor(c_ // 8, lvl, N.RY_F32)), P.full(P.tensor(c_ // 8, lvl, N.RY_F32))
-            P.conv(L.i, *W(f'{p}.cv1.conv'), x, ta)
+            P.conv_pair(L.i, W(f'{p}.cv1.conv'), W(f'{p}.cv2.conv'), x, ta, (cat, c_, c_))
             attention(L.i, f'{p}.m', N.OP_CRISSCROSS, ta, tb, q, k)
             attention(L.i, f'{p}.m1', N.OP_VERTICAL, tb, (cat, 0, c_), q, k)
-            P.conv(L.i, *W(f'{p}.cv2.conv'), x, (cat, c_, c_))
             tgt = nxt if bvec is not None else L
             dst = out_view(tgt, lvl)
             P.conv(L.i, *W(f'{p}.cv3.conv'), P.full(cat), dst, bvec=bvec)

@@ -73,7 +73,8 @@ def test_lowering_invariants(oracle_model):
     P = planner.lower(m._layers, m._fused, 1)
     kinds = [o.kind for o in P.ops]
     n_chain = sum(1 + o.n_post for o in P.ops if o.kind == N.OP_CONV_CHAIN)                        # fused 3x3 -> 1x1 [-> 1x1]
-    assert kinds.count(N.OP_CONV) + kinds.count(N.OP_DETECT) + kinds.count(N.OP_STEM) + n_chain == 130   # dense convs
+    n_pair = sum(1 for o in P.ops if o.kind == N.OP_CONV and o.out1.tensor >= 0 and o.out1.tensor != o.out0.tensor)   # cv1 + cv2 merged
+    assert kinds.count(N.OP_CONV) + kinds.count(N.OP_DETECT) + kinds.count(N.OP_STEM) + n_chain + n_pair == 130   # dense convs
     assert kinds.count(N.OP_DW5) == 18 and kinds.count(N.OP_MAXPOOL2) == 6 and kinds.count(N.OP_UPSAMPLE2) == 2
     assert kinds.count(N.OP_CRISSCROSS) == 6 and kinds.count(N.OP_VERTICAL) == 6 and kinds.count(N.OP_CA) == 6
     written = {}
