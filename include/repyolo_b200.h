@@ -66,7 +66,7 @@ enum ry_op_kind {
     RY_OP_SPP = 5,        /* 5/9/13 s1 max-pools, written at three channel offsets               (SPPCSPC.m)       */
     RY_OP_UPSAMPLE2 = 6,  /* nearest x2                                                          (nn.Upsample)     */
     RY_OP_CA = 7,         /* global avg-pool + f1/ReLU + f2/sigmoid, out = p*s + p -> VEC         (CA)              */
-    RY_OP_ATTN_QK = 8,    /* grouped 1x1 q/k convs + SiLU + shared BN + ReLU6 -> fp32 q,k         (attention q/k)   */
+    RY_OP_ATTN_QK = 8,    /* (stand-alone q/k projection -> fp32 q,k; the planner fuses it into ops 9/10 instead)          */
     RY_OP_CRISSCROSS = 9, /* CrissCrossAttention core: gamma*out + x                                                */
     RY_OP_VERTICAL = 10,  /* VerticalAttention core:   gamma*out + x                                                */
     RY_OP_DETECT = 11,    /* head 1x1 conv on tcgen05 + sigmoid/grid/anchor decode -> pred + raw  (IDetect)         */
@@ -102,7 +102,8 @@ typedef struct ry_op_desc {
     int64_t b_off;         /*   CONV/STEM/DETECT: w = fp32 [cout][cin][k][k] (PyTorch OIHW), b = fp32 [cout]        */
     int64_t aux_off[6];    /*   DW5: w = fp32 [C][5][5]; CA: w = f1 [C/16][C], aux0 = f2 [C][C/16];                 */
                            /*   ATTN_QK: w = wq [Cq][8], b = bq, aux0 = wk, aux1 = bk, aux2/3 = shared BN scale/shift*/
-                           /*   CRISSCROSS/VERTICAL: w = wv [C], b = bv [C], aux0/1 = BN1 scale/shift [C]           */
+                           /*   CRISSCROSS/VERTICAL: w = wv [C], b = bv [C], aux0/1 = BN1 scale/shift [C], aux2 = packed q/k   */
+                           /*   projection (C/8 x 20 fp32): wq [Cq][8] | bq | wk [Cq][8] | bk | shared BN scale | shift      */
     float fparam[8];       /* CRISSCROSS/VERTICAL: [0] = gamma;  DETECT: [0] = stride, [1..6] = anchor (w,h) x 3    */
 } ry_op_desc;
 

@@ -111,20 +111,45 @@ __global__ void __launch_bounds__(NT * 16 * LPC) attn_mma_kernel(const AttnParam
     // ---- stage operands ----
     if (MODE != MODE_VPV && active) {
         // Aq row = [Qhi | Qhi | Qlo | 0], Bk row = [Khi | Klo | Khi | 0]  ->  Aq.Bk^T = Qhi.Khi + Qhi.Klo + Qlo.Khi
+        // q = ReLU6(bn(SiLU(gconv_q(x)))), k likewise with the SAME bn (common.py:3693-3701), computed here from the 8 input
+        // channels of group d -- the same 16 bytes of x that give the 8 value channels v[8d..8d+7] (no q/k round trip through HBM)
         const __nv_bfloat16 zero = __float2bfloat16_rn(0.0f);
-        for (int idx = tis; idx < LP * Cq; idx += kThreads) {            // each q / k element is read once
+        const float *wq = p.qk, *bq = wq + Cq * 8, *wk = bq + Cq, *bk = wk + Cq * 8, *qs = bk + Cq, *qt = qs + Cq;
+        for (int idx = tis; idx < LP * Cq; idx += kThreads) {
             const int pi = idx / Cq, d = idx - pi * Cq;
             float qa = 0.0f, kb = 0.0f;
+            uint4 vo = make_uint4(0, 0, 0, 0);
             if (pi < L) {
-                const size_t px = pix_of(pi);
-                qa = __ldg(p.q + px * Cq + d);
-                kb = __ldg(p.k + px * Cq + d);
+                const uint4 u = __ldg(reinterpret_cast<const uint4 *>(p.x + pix_of(pi) * p.x_cs + p.x_off + d * 8));
+                const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
+                const float xv[8] = {f0.x, f0.y, f1.x, f1.y, f2.x, f2.y, f3.x, f3.y};
+                float aq = __ldg(bq + d), ak = __ldg(bk + d);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    aq = fmaf(__ldg(wq + d * 8 + j), xv[j], aq);
+                    ak = fmaf(__ldg(wk + d * 8 + j), xv[j], ak);
+                }
+                const float sc = __ldg(qs + d), sh = __ldg(qt + d);
+                qa = relu6_f(fmaf(sc, silu_f(aq), sh));
+                kb = relu6_f(fmaf(sc, silu_f(ak), sh));
+                if (MODE != MODE_VE) {
+                    uint32_t ow[4];
+#pragma unroll
+                    for (int h = 0; h < 4; ++h) {
+                        const int c0 = d * 8 + 2 * h;
+                        ow[h] = pack_bf16x2(v_of(xv[2 * h], __ldg(p.wv + c0), __ldg(p.bv + c0), __ldg(p.s1 + c0), __ldg(p.t1 + c0)),
+                                            v_of(xv[2 * h + 1], __ldg(p.wv + c0 + 1), __ldg(p.bv + c0 + 1), __ldg(p.s1 + c0 + 1),
+                                                 __ldg(p.t1 + c0 + 1)));
+                    }
+                    vo = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+                }
             }
             const __nv_bfloat16 qh = __float2bfloat16_rn(qa), kh = __float2bfloat16_rn(kb);
             const __nv_bfloat16 ql = __float2bfloat16_rn(qa - __bfloat162float(qh)), kl = __float2bfloat16_rn(kb - __bfloat162float(kh));
             __nv_bfloat16 *ar = Aq + (size_t)pi * sq, *br = Bk + (size_t)pi * sq;
             ar[d] = qh; ar[Cq + d] = qh; ar[2 * Cq + d] = ql;
             br[d] = kh; br[Cq + d] = kl; br[2 * Cq + d] = kh;
+            if (MODE != MODE_VE) *reinterpret_cast<uint4 *>(Vs + (size_t)pi * sv + d * 8) = vo;
         }
         const int padc = KQ - 3 * Cq;
         for (int idx = tis; idx < LP * padc; idx += kThreads) {
@@ -133,7 +158,7 @@ __global__ void __launch_bounds__(NT * 16 * LPC) attn_mma_kernel(const AttnParam
             Bk[(size_t)pi * sq + col] = zero;
         }
     }
-    if (MODE != MODE_VE && active) {
+    if (MODE == MODE_VPV && active) {
         const int vecs = C / 8;
         for (int idx = tis; idx < LP * vecs; idx += kThreads) {
             const int pi = idx / vecs, c = (idx - pi * vecs) * 8;

@@ -26,7 +26,7 @@ struct AttnParams {
     int x_cs, x_off;
     int C, Cq;                // Cq = C / 8
     int B, H, W;
-    const float *q, *k;       // [B, H*W, Cq] fp32 (written by attn_qk_launch)
+    const float *qk;          // packed q/k conv parameters: wq [Cq][8] | bq [Cq] | wk [Cq][8] | bk [Cq] | shared BN scale [Cq] | shift [Cq]
     const float *wv, *bv;     // value conv (depthwise 1x1 folded with its BN): v = relu6(s1 * silu(wv*x + bv) + t1)
     const float *s1, *t1;     // stand-alone BN1 as scale/shift
     float gamma;

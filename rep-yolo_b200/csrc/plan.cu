@@ -634,7 +634,7 @@ int run_op(ry_plan *p, Op &op, const float *image, float *pred, float *raws[3], 
             AttnParams ap;
             ap.x = bf(p, d.in0.tensor); ap.x_cs = ti.d.channels; ap.x_off = d.in0.c_off;
             ap.C = d.cin; ap.Cq = d.cin / 8; ap.B = B; ap.H = ti.h; ap.W = ti.w;
-            ap.q = f32(p, d.in1.tensor); ap.k = f32(p, d.in2.tensor);
+            ap.qk = wf(p, op.dev[4]);
             ap.wv = wf(p, op.dev[0]); ap.bv = wf(p, op.dev[1]); ap.s1 = wf(p, op.dev[2]); ap.t1 = wf(p, op.dev[3]);
             ap.gamma = d.fparam[0];
             ap.out = bf(p, d.out0.tensor); ap.out_cs = to.d.channels; ap.out_off = d.out0.c_off;
@@ -756,7 +756,8 @@ int ry_plan_create(const ry_tensor_desc *tensors, int n_tensors, const ry_op_des
                 const int C = d.cin;
                 rc = copy_f32(host, weight_bytes, d.w_off, C, blob, &op.dev[0]) || copy_f32(host, weight_bytes, d.b_off, C, blob, &op.dev[1]) ||
                      copy_f32(host, weight_bytes, d.aux_off[0], C, blob, &op.dev[2]) ||
-                     copy_f32(host, weight_bytes, d.aux_off[1], C, blob, &op.dev[3]);
+                     copy_f32(host, weight_bytes, d.aux_off[1], C, blob, &op.dev[3]) ||
+                     copy_f32(host, weight_bytes, d.aux_off[2], (size_t)(C / 8) * 20, blob, &op.dev[4]);   // packed q/k conv parameters
                 break;
             }
             default: break;

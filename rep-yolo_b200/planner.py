@@ -192,10 +192,9 @@ def lower(layers, fz, nc=1, fuse_chains=None):
         s1, t1 = bn_affine(fz, f'{p}.bn1')
         C, Cq = wv.shape[0], wq.shape[0]
         assert wq.shape[1] == 8 and wv.shape[1] == 1
-        P.op(N.OP_ATTN_QK, layer, in0=src, out0=q, out1=k, cin=C, cout=Cq, w_off=P.blob.add(wq.reshape(Cq, 8)),
-             b_off=P.blob.add(bq), aux=[P.blob.add(wk.reshape(Cq, 8)), P.blob.add(bk), P.blob.add(s), P.blob.add(t)])
-        P.op(kind, layer, in0=src, in1=q, in2=k, out0=dst, cin=C, cout=C, w_off=P.blob.add(wv.reshape(C)),
-             b_off=P.blob.add(bv), aux=[P.blob.add(s1), P.blob.add(t1)], fparam=[float(fz[f'{p}.gamma'].item())])
+        qk_pack = torch.cat([wq.reshape(-1), bq.reshape(-1), wk.reshape(-1), bk.reshape(-1), s.reshape(-1), t.reshape(-1)])
+        P.op(kind, layer, in0=src, out0=dst, cin=C, cout=C, w_off=P.blob.add(wv.reshape(C)),
+             b_off=P.blob.add(bv), aux=[P.blob.add(s1), P.blob.add(t1), P.blob.add(qk_pack)], fparam=[float(fz[f'{p}.gamma'].item())])
 
     skip = set()
     for L in layers:
@@ -300,7 +299,7 @@ def lower(layers, fz, nc=1, fuse_chains=None):
                 g.inputs.append((L.i - 1, bvec))
             cat = P.tensor(2 * c_, lvl)
             ta, tb = P.full(P.tensor(c_, lvl)), P.full(P.tensor(c_, lvl))
-            q, k = P.full(P.tensor(c_ // 8, lvl, N.RY_F32)), P.full(P.tensor(c_ // 8, lvl, N.RY_F32))
+            q = k = None                                 # q/k projections are fused into the attention kernels
             P.conv_pair(L.i, W(f'{p}.cv1.conv'), W(f'{p}.cv2.conv'), x, ta, (cat, c_, c_))
             attention(L.i, f'{p}.m', N.OP_CRISSCROSS, ta, tb, q, k)
             attention(L.i, f'{p}.m1', N.OP_VERTICAL, tb, (cat, 0, c_), q, k)
