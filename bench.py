@@ -35,45 +35,67 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
-         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+    """SM clock / throttle reasons sampled DURING the timed region through NVML (every 5 ms, same counters `nvidia-smi
+    --query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.*` prints; nvidia-smi itself block-buffers a piped stdout)."""
+    REASONS = (('hw_slowdown', 0x8), ('hw_thermal_slowdown', 0x40), ('sw_thermal_slowdown', 0x20), ('sw_power_cap', 0x4))
 
-    def __init__(self, index):
+    def __init__(self, index, uuid=None):
         super().__init__(daemon=True)
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.uuid, self.rows, self.halt, self.max_mhz = index, uuid, [], threading.Event(), None
 
     def run(self):
         try:
-            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
-                                          '-lms', '50'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            for line in self.proc.stdout:
-                self.rows.append([c.strip() for c in line.split(',')])
+            import pynvml as nv
+            nv.nvmlInit()
+            h = None
+            if self.uuid:
+                try:
+                    h = nv.nvmlDeviceGetHandleByUUID(('GPU-' + self.uuid).encode())
+                except Exception:
+                    h = None
+            if h is None:
+                vis = os.environ.get('CUDA_VISIBLE_DEVICES', '')
+                ids = [v for v in vis.split(',') if v.strip().isdigit()]
+                h = nv.nvmlDeviceGetHandleByIndex(int(ids[self.index]) if self.index < len(ids) else self.index)
+            self.max_mhz = int(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            while not self.halt.is_set():
+                try:
+                    r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                except Exception:
+                    r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                self.rows.append((int(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), r))
+                time.sleep(0.005)
         except Exception:
-            pass
+            self._smi_fallback()
 
-    def wait_first(self, timeout=5.0):
-        """nvidia-smi needs ~0.3-1 s to deliver its first row: block until it has, so a short timed region is covered"""
+    def _smi_fallback(self):
+        q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+        while not self.halt.is_set():
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), f'--query-gpu={q}', '--format=csv,noheader,nounits'],
+                                     capture_output=True, text=True, timeout=10).stdout.strip().splitlines()[0]
+                c = [v.strip() for v in out.split(',')]
+                self.max_mhz = int(c[1])
+                bits = sum(b for (_, b), v in zip(self.REASONS, c[2:6]) if v.lower().startswith('active'))
+                self.rows.append((int(c[0]), bits))
+            except Exception:
+                time.sleep(0.05)
+
+    def wait_first(self, timeout=10.0):
         t0 = time.perf_counter()
         while not self.rows and time.perf_counter() - t0 < timeout:
-            time.sleep(0.02)
+            time.sleep(0.005)
 
     def mark(self):
         return len(self.rows)
 
     def stop(self, first=0):
-        if self.proc:
-            self.proc.terminate()
-        self.rows = self.rows[first:]
-        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
-        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
-        reasons = set()
-        for r in self.rows:
-            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[3:7]):
-                if v.lower().startswith('active'):
-                    reasons.add(name)
-        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-                'reasons': sorted(reasons), 'samples': len(sm)}
+        self.halt.set()
+        rows = self.rows[first:]
+        sm = sorted(r[0] for r in rows)
+        reasons = sorted({name for name, bit in self.REASONS for r in rows if r[1] & bit})
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': self.max_mhz, 'reasons': reasons, 'samples': len(sm)}
 
 
 def oracle_step(fz, layers, save, x, torch, O, nms_oracle):
@@ -168,7 +190,7 @@ def run_native(args):
             torch.cuda.synchronize(dev)
 
     # ---- kernel-resident throughput (inputs already in HBM) ----
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(local, str(getattr(torch.cuda.get_device_properties(dev), 'uuid', '') or ''))
     sampler.start()
     for i in range(args.warmup):
         step(xdev[i % n_bufs])
@@ -249,7 +271,7 @@ def run_native(args):
             hi, wi = S >> lvl, S >> lvl
             ho, wo = hi // d.stride, wi // d.stride
             fl = 2.0 * d.cout * d.cin * d.ksize * d.ksize * ho * wo * B
-            by = 2.0 * B * (hi * wi * d.cin + ho * wo * d.cout) if d.kind == 2 else B * (2.0 * hi * wi * d.cin + 8.0 * ho * wo * d.cout)
+            by = 2.0 * B * (hi * wi * d.cin + ho * wo * d.cout / (4 if d.level_idx == 1 else 1)) if d.kind == 2 else B * (2.0 * hi * wi * d.cin + 8.0 * ho * wo * d.cout)
             if d.kind == 12:          # fused chain: all stages' MACs; bytes = input + the outputs that are actually stored
                 prev, outs = d.cout, [d.out0, d.out1, d.out2]
                 by = 2.0 * B * hi * wi * d.cin + sum(2.0 * B * hi * wi * o.c_len for o in outs if o.tensor >= 0)

@@ -91,7 +91,8 @@ typedef struct ry_op_desc {
     int32_t stride;        /* 1 or 2 */
     int32_t act;           /* ry_act */
     int32_t cin, cout;
-    int32_t level_idx;     /* DETECT: pyramid level (row offset / stride / anchors) */
+    int32_t level_idx;     /* DETECT: pyramid level (row offset / stride / anchors); CONV (1x1): 1 = MaxPool2d(2,2) of the    */
+                           /* activated output fused in the epilogue, out0 is then the pooled map (MP after DER_Block.cv1)   */
     int32_t n_src;         /* CONV: number of concatenated input views (0 or 1 = just in0) */
     int32_t pad_;
     int32_t n_post;        /* CONV_CHAIN: number of fused 1x1 stages (1 or 2); their weights/biases are aux_off[0..3]     */

@@ -293,11 +293,40 @@ __device__ __forceinline__ void epilogue_store_role(const ConvArgs &p, const Epi
                     st_shared_v4(buf + lin, o);
                 }
             }
+            if (p.pool) {
+                // fused MaxPool2d(2, 2): the 128-pixel tile is tw x th (both even); 2x2 windows reduced from the staged tile into
+                // a 32-pixel pooled tile behind it (same row width / swizzle), which is what the TMA store sends out
+                ptx::bar_sync(1 + grp, 128);
+                const int cpr = sg.ncol >> 3, rbs = sg.ncol * 2, hw = p.tw >> 1, hh = p.th >> 1;
+                const uint32_t pbuf = buf + 128u * (uint32_t)rbs;
+                for (int idx = (e & 3) * 32 + lane; idx < hw * hh * p.tn * cpr; idx += 128) {
+                    const int prow = idx / cpr, ch = idx - prow * cpr;
+                    const int pyn = prow / hw, px = prow - pyn * hw;          // pyn = pn * hh + py: source row 2 * pyn of the tile
+                    const int r0 = 2 * pyn * p.tw + 2 * px;
+                    uint4 m = make_uint4(0, 0, 0, 0);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int r = r0 + (q & 1) + (q >> 1) * p.tw;
+                        uint32_t lin = (uint32_t)(r * rbs + ch * 16);
+                        lin ^= ((lin >> 7) & swz) << 4;
+                        uint4 v;
+                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(buf + lin));
+                        m = q == 0 ? v : bf16x8_max(m, v);
+                    }
+                    uint32_t lo = (uint32_t)(prow * rbs + ch * 16);
+                    lo ^= ((lo >> 7) & swz) << 4;
+                    st_shared_v4(pbuf + lo, m);
+                }
+            }
             ptx::fence_proxy_async();
             ptx::bar_sync(1 + grp, 128);
             if (leader) {
-                ptx::tma_store_4d(p.omap + sg.map, reinterpret_cast<const void *>(cx.sStage + (size_t)(grp * nbuf + bufsel) * p.stage_buf_bytes),
-                                  sg.chan + tc.nc0, tc.w0, tc.h0, tc.n0);
+                const uint8_t *src = cx.sStage + (size_t)(grp * nbuf + bufsel) * p.stage_buf_bytes;
+                if (p.pool)
+                    ptx::tma_store_4d(p.omap + sg.map, reinterpret_cast<const void *>(src + 128 * sg.ncol * 2), sg.chan + tc.nc0, tc.w0 >> 1,
+                                      tc.h0 >> 1, tc.n0);
+                else
+                    ptx::tma_store_4d(p.omap + sg.map, reinterpret_cast<const void *>(src), sg.chan + tc.nc0, tc.w0, tc.h0, tc.n0);
                 ptx::bulk_commit();
             }
             if (nbuf == 2) bufsel ^= 1;
@@ -494,7 +523,7 @@ int conv_plan_smem(ConvArgs &a, int max_seg_cols) {
     a.a_box_bytes = box_rows * rb;
     a.a_stage_bytes = a.a_mode == A_HALO ? ((a.a_box_bytes + 1023) & ~1023) : 128 * rb;
     a.b_stage_bytes = a.BN * rb;
-    a.stage_buf_bytes = a.mode == 0 ? ((128 * max_seg_cols * 2 + 1023) & ~1023) : 0;
+    a.stage_buf_bytes = a.mode == 0 ? (((a.pool ? 160 : 128) * max_seg_cols * 2 + 1023) & ~1023) : 0;   // + pooled tile behind it
     const long fixed = 4L * a.stage_buf_bytes + ((a.cout_pad * 4 + 127) & ~127) + kBarrierBytes + 1024;
     const long avail = kSmemLimit - fixed;
     const long b_total = (long)a.kblocks * a.b_stage_bytes;

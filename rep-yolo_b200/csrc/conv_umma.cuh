@@ -67,6 +67,8 @@ struct ConvArgs {
     int b_stage_bytes, b_stages, b_resident;
     int n_acc;                 // TMEM accumulator stages: 2 or 4 (4 * BN <= 512)
     int stage_buf_bytes;       // epilogue staging: n_groups x (2 buffers, or 1 when n_groups == 4) of this size
+    int pool;                  // 1: MaxPool2d(2,2) of the activated tile fused in the epilogue (MP after DER_Block.cv1); the
+                               //    staged tile is reduced 2x2 in shared memory and only the pooled tile is stored
     int mode;                  // 0 = bf16 NHWC store, 1 = Detect decode
     int ep_teams;              // 1: the 4-warp epilogue groups take alternate TILES (small N); 0: disjoint COLUMNS of each tile
     int n_groups;              // epilogue groups: 2, or 4 (tile teams of the memory-bound small-N layers)

@@ -12,6 +12,11 @@ namespace ry {
 
 namespace {
 
+__device__ __forceinline__ float tanh_approx_f(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ uint4 ldg16(const __nv_bfloat16 *p) { return __ldg(reinterpret_cast<const uint4 *>(p)); }
 __device__ __forceinline__ void stg16(__nv_bfloat16 *p, uint4 v) { *reinterpret_cast<uint4 *>(p) = v; }
 
@@ -188,88 +193,158 @@ __global__ void __launch_bounds__(256) stem_kernel(const void *__restrict__ img_
 // ------------------------------------------------------------------------------------------------------------------
 // Depthwise 5x5 s1 p2 + bias + act  (GSConv.cv2, reference models/common.py:3813, 3817).  Channels come as two halves
 // (in_off0 / in_off1) and go to two halves (out_off0 / out_off1): the GSConv channel shuffle folded into addressing.
-// One CTA = one spatial tile (TH rows x TWP pixels) x 32 channels: the (TH+4) x (TWP+4) halo is staged once in shared
-// memory (each input crosses L1/L2 once instead of 25 times); one thread = 8 channels x a strip of 4 pixels of one row,
-// so every staged vector is reused by up to 5 x 4 taps from registers.  weights: [25][C] fp32 (tap-major).
+// Persistent CTAs over (image, spatial tile, 32-channel group) work items, two cp.async stages: the (TH+4) x (TW+4)
+// halo of the NEXT item (zero-filled outside the map = the conv padding), its 25 x 32 weights and bias land in shared
+// memory while the current item is computed.  A warp = 8 rows x one strip of 4 pixels; lane = (row, 8-channel vector);
+// the halo row pitch is an odd number of pixels so that the 8 lanes of a quarter warp hit 8 different 16-byte bank
+// groups.  Every staged vector feeds up to 5 x 4 taps from registers; the MACs are packed fp32 pairs (FFMA2).
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int kDwThreads = 256;
-constexpr int kDwCv = 4;                       // 8-channel vectors per CTA (32 channels)
+struct Dw5Args {
+    const __nv_bfloat16 *in;
+    __nv_bfloat16 *out;
+    const float *w, *bias;          // [25][C] (tap-major), [C]
+    int in_cs, in_off0, in_off1, out_cs, out_off0, out_off1;
+    int C, half, H, W, act;
+    int SX, RG;                     // warps: SX strips of 4 pixels x RG groups of 8 rows
+    int pitch;                      // halo row pitch in pixels (odd)
+    int tiles_x, tiles_y, n_items, stage_bytes, halo_bytes;
+};
 
-__global__ void __launch_bounds__(kDwThreads) dw5_kernel(const __nv_bfloat16 *__restrict__ in, int in_cs, int in_off0, int in_off1,
-                                                         __nv_bfloat16 *__restrict__ out, int out_cs, int out_off0, int out_off1,
-                                                         const float *__restrict__ w, const float *__restrict__ bias, int C,
-                                                         int half, int H, int W, int act, int twp, int th, int tiles_x,
-                                                         int tiles_y) {
-    pdl_trigger();
-    pdl_wait();
-    extern __shared__ __align__(16) uint8_t dw_smem[];
-    const int hw_ = twp + 4;                                   // halo row length in pixels
-    uint4 *tile = reinterpret_cast<uint4 *>(dw_smem);          // [(th+4)][hw_][kDwCv] 16-byte vectors
-    float *sw = reinterpret_cast<float *>(tile + (size_t)(th + 4) * hw_ * kDwCv);   // [25][32]
-    float *sb = sw + 25 * 32;                                  // [32]
-    int bid = blockIdx.x;
-    const int cg = bid % (C / 32); bid /= (C / 32);
-    const int tx = bid % tiles_x; bid /= tiles_x;
-    const int ty = bid % tiles_y;
-    const int b = bid / tiles_y;
-    const int x0 = tx * twp, y0 = ty * th, c0 = cg * 32;
-    for (int i = threadIdx.x; i < 25 * 32; i += kDwThreads) sw[i] = __ldg(w + (i / 32) * C + c0 + (i & 31));
-    if (threadIdx.x < 32) sb[threadIdx.x] = __ldg(bias + c0 + threadIdx.x);
-    const size_t img_base = (size_t)b * H * W;
-    for (int i = threadIdx.x; i < (th + 4) * hw_ * kDwCv; i += kDwThreads) {
-        const int v = i % kDwCv, px = (i / kDwCv) % hw_, py = i / (kDwCv * hw_);
-        const int yy = y0 + py - 2, xx = x0 + px - 2;
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, bool ok) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16 : 0) : "memory");   // !ok: zero fill
+}
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ float2 unpack_f32x2(uint64_t v) {
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+// two bf16 of one 32-bit word -> exact fp32 pair
+__device__ __forceinline__ uint64_t bf16x2_to_f32x2(uint32_t u) {
+    return pack_f32x2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+}
+
+__device__ __forceinline__ void dw5_stage_load(const Dw5Args &a, uint32_t base, int item) {
+    const int ncg = a.C >> 5;
+    const int cg = item % ncg; item /= ncg;
+    const int tx = item % a.tiles_x; item /= a.tiles_x;
+    const int ty = item % a.tiles_y;
+    const int b = item / a.tiles_y;
+    const int twp4 = 4 * a.SX + 4, th4 = 8 * a.RG + 4;
+    const int x0 = tx * 4 * a.SX - 2, y0 = ty * 8 * a.RG - 2, c0 = cg * 32;
+    const size_t img_base = (size_t)b * a.H * a.W;
+    for (int i = threadIdx.x; i < th4 * twp4 * 4; i += blockDim.x) {
+        const int v = i & 3, q = i >> 2;
+        const int py = q / twp4, px = q - py * twp4;
+        const int yy = y0 + py, xx = x0 + px;
         const int c = c0 + v * 8;
-        const int ci = c < half ? in_off0 + c : in_off1 + (c - half);
-        uint4 u = make_uint4(0, 0, 0, 0);
-        if (yy >= 0 && yy < H && xx >= 0 && xx < W) u = ldg16(in + (img_base + (size_t)yy * W + xx) * in_cs + ci);
-        tile[i] = u;
+        const int ci = c < a.half ? a.in_off0 + c : a.in_off1 + (c - a.half);
+        const bool ok = yy >= 0 && yy < a.H && xx >= 0 && xx < a.W;
+        const __nv_bfloat16 *src = a.in + (ok ? (img_base + (size_t)yy * a.W + xx) * a.in_cs + ci : 0);
+        cp_async16(base + (uint32_t)(((py * a.pitch + px) * 4 + v) * 16), src, ok);
     }
-    __syncthreads();
-    const int v = threadIdx.x % kDwCv, strip = threadIdx.x / kDwCv;
-    const int strips_x = twp / 4;
-    const int sy = strip / strips_x, sx = (strip - sy * strips_x) * 4;
-    if (sy >= th) return;
-    float acc[4][8];
+    for (int i = threadIdx.x; i < 25 * 8 + 8; i += blockDim.x) {         // weights [25][32] fp32, then bias [32]
+        const float *src = i < 200 ? a.w + (size_t)(i >> 3) * a.C + c0 + (i & 7) * 4 : a.bias + c0 + (i - 200) * 4;
+        cp_async16(base + (uint32_t)a.halo_bytes + (uint32_t)i * 16, src, true);
+    }
+}
+
+__global__ void __launch_bounds__(512, 1) dw5_kernel(const __grid_constant__ Dw5Args a) {
+    pdl_trigger();
+    extern __shared__ __align__(128) uint8_t dw_smem[];
+    const uint32_t smem_u = (uint32_t)__cvta_generic_to_shared(dw_smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int v = lane & 3, ry = lane >> 2;
+    const int sxi = warp % a.SX, rgi = warp / a.SX;
+    const int r = rgi * 8 + ry, sx = sxi * 4;
+    const int ncg = a.C >> 5;
+    pdl_wait();
+    int item = blockIdx.x, stage = 0;
+    if (item < a.n_items) dw5_stage_load(a, smem_u, item);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    for (; item < a.n_items; item += gridDim.x, stage ^= 1) {
+        if (item + (int)gridDim.x < a.n_items) dw5_stage_load(a, smem_u + (stage ^ 1) * a.stage_bytes, item + gridDim.x);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncthreads();
+        const uint8_t *base = dw_smem + (size_t)stage * a.stage_bytes;
+        const float *sw = reinterpret_cast<const float *>(base + a.halo_bytes) + v * 8;
+        uint64_t acc[4][4];
+        {
+            const float4 b0 = *reinterpret_cast<const float4 *>(sw + 25 * 32), b1 = *reinterpret_cast<const float4 *>(sw + 25 * 32 + 4);
 #pragma unroll
-    for (int p = 0; p < 4; ++p)
-#pragma unroll
-        for (int k = 0; k < 8; ++k) acc[p][k] = sb[v * 8 + k];
+            for (int p = 0; p < 4; ++p) {
+                acc[p][0] = pack_f32x2(b0.x, b0.y); acc[p][1] = pack_f32x2(b0.z, b0.w);
+                acc[p][2] = pack_f32x2(b1.x, b1.y); acc[p][3] = pack_f32x2(b1.z, b1.w);
+            }
+        }
+        const uint4 *row = reinterpret_cast<const uint4 *>(base) + ((size_t)r * a.pitch + sx) * 4 + v;
 #pragma unroll 1
-    for (int dy = 0; dy < 5; ++dy) {
-        float xin[8][8];
-        const uint4 *row = tile + ((size_t)(sy + dy) * hw_ + sx) * kDwCv + v;
+        for (int dy = 0; dy < 5; ++dy) {
+            uint64_t wk[5][4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const uint4 u = row[j * kDwCv];
-            const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
-            xin[j][0] = f0.x; xin[j][1] = f0.y; xin[j][2] = f1.x; xin[j][3] = f1.y;
-            xin[j][4] = f2.x; xin[j][5] = f2.y; xin[j][6] = f3.x; xin[j][7] = f3.y;
+            for (int dx = 0; dx < 5; ++dx) {
+                const float4 w0 = *reinterpret_cast<const float4 *>(sw + (dy * 5 + dx) * 32);
+                const float4 w1 = *reinterpret_cast<const float4 *>(sw + (dy * 5 + dx) * 32 + 4);
+                wk[dx][0] = pack_f32x2(w0.x, w0.y); wk[dx][1] = pack_f32x2(w0.z, w0.w);
+                wk[dx][2] = pack_f32x2(w1.x, w1.y); wk[dx][3] = pack_f32x2(w1.z, w1.w);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {                       // input pixel sx - 2 + j of this halo row
+                const uint4 u = row[j * 4];
+                const uint64_t x0 = bf16x2_to_f32x2(u.x), x1 = bf16x2_to_f32x2(u.y), x2 = bf16x2_to_f32x2(u.z), x3 = bf16x2_to_f32x2(u.w);
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                    const int dx = j - p;
+                    if (dx >= 0 && dx < 5) {
+                        acc[p][0] = ffma2(x0, wk[dx][0], acc[p][0]);
+                        acc[p][1] = ffma2(x1, wk[dx][1], acc[p][1]);
+                        acc[p][2] = ffma2(x2, wk[dx][2], acc[p][2]);
+                        acc[p][3] = ffma2(x3, wk[dx][3], acc[p][3]);
+                    }
+                }
+            }
+            row += (size_t)a.pitch * 4;
         }
+        {
+            int it = item;
+            const int cg = it % ncg; it /= ncg;
+            const int tx = it % a.tiles_x; it /= a.tiles_x;
+            const int ty = it % a.tiles_y;
+            const int b = it / a.tiles_y;
+            const int y = ty * 8 * a.RG + r, xb = tx * 4 * a.SX + sx;
+            const int c = cg * 32 + v * 8;
+            const int co = c < a.half ? a.out_off0 + c : a.out_off1 + (c - a.half);
+            if (y < a.H) {
+                __nv_bfloat16 *orow = a.out + (((size_t)b * a.H + y) * a.W + xb) * a.out_cs + co;
 #pragma unroll
-        for (int dx = 0; dx < 5; ++dx) {
-            const float4 w0 = *reinterpret_cast<const float4 *>(sw + (dy * 5 + dx) * 32 + v * 8);
-            const float4 w1 = *reinterpret_cast<const float4 *>(sw + (dy * 5 + dx) * 32 + v * 8 + 4);
-            const float wk[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+                for (int p = 0; p < 4; ++p) {
+                    if (xb + p >= a.W) break;
+                    uint32_t o[4];
 #pragma unroll
-            for (int p = 0; p < 4; ++p)
-#pragma unroll
-                for (int k = 0; k < 8; ++k) acc[p][k] = fmaf(xin[p + dx][k], wk[k], acc[p][k]);
+                    for (int k = 0; k < 4; ++k) {
+                        float2 f = unpack_f32x2(acc[p][k]);
+                        if (a.act == 1) {                        // SiLU(x) = h + h * tanh(h), h = x / 2
+                            const float h0 = 0.5f * f.x, h1 = 0.5f * f.y;
+                            f.x = fmaf(h0, tanh_approx_f(h0), h0);
+                            f.y = fmaf(h1, tanh_approx_f(h1), h1);
+                        }
+                        o[k] = pack_bf16x2(f.x, f.y);
+                    }
+                    stg16(orow + (size_t)p * a.out_cs, make_uint4(o[0], o[1], o[2], o[3]));
+                }
+            }
         }
-    }
-    const int y = y0 + sy;
-    if (y >= H) return;
-    const int c = c0 + v * 8;
-    const int co = c < half ? out_off0 + c : out_off1 + (c - half);
-#pragma unroll
-    for (int p = 0; p < 4; ++p) {
-        const int x = x0 + sx + p;
-        if (x >= W) break;
-        float r[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) r[k] = act == 1 ? silu_f(acc[p][k]) : acc[p][k];
-        stg16(out + (img_base + (size_t)y * W + x) * out_cs + co,
-              make_uint4(pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]), pack_bf16x2(r[4], r[5]), pack_bf16x2(r[6], r[7])));
+        __syncthreads();                                          // this stage is refilled by the next iteration's prefetch
     }
 }
 
@@ -465,26 +540,41 @@ int stem_launch(const void *img, int img_u8, const float *w27, const float *bias
 void dw5_launch(const __nv_bfloat16 *in, int in_cs, int in_off0, int in_off1, __nv_bfloat16 *out, int out_cs, int out_off0,
                 int out_off1, const float *w, const float *bias, int C, int half, int B, int H, int W, int act,
                 cudaStream_t st) {
-    // tile: up to 64 strips of 4 pixels; pick the strip layout that wastes the fewest threads / halo pixels
-    int best_twp = 4, best_th = 1;
+    // tile = (4 SX) x (8 RG) pixels, SX * RG warps.  Model: an SM issues for ~16 warps at a time, so one round of n resident
+    // CTAs costs n * warps; rounds = ceil(items / (148 n)); staged halo pixels per output pixel add L2 -> smem traffic.
+    Dw5Args a = {};
     double best = -1.0;
-    for (int sx = 1; sx <= 16; ++sx) {
-        const int twp = sx * 4, th = std::min(64 / sx, H);
-        if (twp - 3 > W && sx > 1) break;
-        const int tiles = cdiv(W, twp) * cdiv(H, th);
-        const double useful = (double)H * W / ((double)tiles * (th + 4) * (twp + 4));   // output pixels per staged pixel
-        if (useful > best) { best = useful; best_twp = twp; best_th = th; }
-    }
-    const int tiles_x = cdiv(W, best_twp), tiles_y = cdiv(H, best_th);
-    const size_t smem = (size_t)(best_th + 4) * (best_twp + 4) * kDwCv * 16 + (25 * 32 + 32) * sizeof(float);
+    for (int sx = 1; sx <= 16; ++sx)
+        for (int rg = 1; rg * sx <= 16; ++rg) {
+            const int warps = sx * rg;
+            if (warps < 4 && !(4 * sx >= W && 8 * rg >= H)) continue;
+            const int pitch = 4 * sx + 5;
+            const size_t stage = ((size_t)(8 * rg + 4) * pitch * 64 + 208 * 16 + 127) & ~(size_t)127;
+            if (2 * stage > 200 * 1024) continue;
+            const int n_res = std::max(1, std::min((int)(220 * 1024 / (2 * stage)), 16 / warps));
+            const long items = (long)B * cdiv(W, 4 * sx) * cdiv(H, 8 * rg) * (C / 32);
+            const double rounds = (double)((items + (long)kNumSMs * n_res - 1) / ((long)kNumSMs * n_res));
+            const double halo = (double)(8 * rg + 4) * (4 * sx + 4) / (32.0 * warps);
+            const double cost = rounds * n_res * warps * (1.0 + 0.08 * halo);
+            if (best < 0 || cost < best) {
+                best = cost;
+                a.SX = sx; a.RG = rg; a.pitch = pitch; a.stage_bytes = (int)stage;
+                a.halo_bytes = (8 * rg + 4) * pitch * 64;
+                a.tiles_x = cdiv(W, 4 * sx); a.tiles_y = cdiv(H, 8 * rg);
+                a.n_items = (int)items;
+            }
+        }
+    a.in = in; a.out = out; a.w = w; a.bias = bias;
+    a.in_cs = in_cs; a.in_off0 = in_off0; a.in_off1 = in_off1; a.out_cs = out_cs; a.out_off0 = out_off0; a.out_off1 = out_off1;
+    a.C = C; a.half = half; a.H = H; a.W = W; a.act = act;
+    const int warps = a.SX * a.RG;
+    const int n_res = std::max(1, std::min((int)(220 * 1024 / (2 * (size_t)a.stage_bytes)), 16 / warps));
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(dw5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        cudaFuncSetAttribute(dw5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr_set = true;
     }
-    launch_pdl(dw5_kernel, dim3(B * tiles_y * tiles_x * (C / 32)), dim3(kDwThreads), smem, st, in, in_cs, in_off0, in_off1, out, out_cs, out_off0, out_off1,
-                                                                         w, bias, C, half, H, W, act, best_twp, best_th, tiles_x,
-                                                                         tiles_y);
+    launch_pdl(dw5_kernel, dim3(std::min(a.n_items, kNumSMs * n_res)), dim3(32 * warps), 2 * (size_t)a.stage_bytes, st, a);
 }
 
 void maxpool2_launch(const __nv_bfloat16 *in, int in_cs, int in_off, __nv_bfloat16 *out, int out_cs, int out_off, int C,

@@ -194,11 +194,12 @@ int copy_f32(const unsigned char *host, size_t host_bytes, int64_t off, size_t n
     return 0;
 }
 
-void pick_tile(int B, int Ho, int Wo, int *tw, int *th, int *tn) {
+void pick_tile(int B, int Ho, int Wo, int *tw, int *th, int *tn, bool even = false) {   // even: 2x2 pooling windows stay inside a tile
     long best_tiles = -1;
     int bw = 1, bh = 1, bn = 1;
-    for (int w = std::min(Wo, 128); w >= 1; --w) {
+    for (int w = std::min(Wo, even ? 64 : 128); w >= 1; --w) {
         for (int h = std::min(Ho, 128 / w); h >= 1; --h) {
+            if (even && ((w | h) & 1)) continue;
             const int n = std::max(1, std::min(B, 128 / (w * h)));
             const long tiles = (long)cdiv(Wo, w) * cdiv(Ho, h) * cdiv(B, n);
             if (best_tiles < 0 || tiles < best_tiles) { best_tiles = tiles; bw = w; bh = h; bn = n; }
@@ -295,6 +296,8 @@ int bind_conv(ry_plan *p, Op &op, std::vector<CUtensorMap> &maps) {
     a.BN = cp.BN; a.n_ntiles = cp.n_ntiles; a.cout_pad = cp.cout_pad;
     a.img_w = Wo; a.img_hw = Ho * Wo;
     a.mode = d.kind == RY_OP_DETECT ? 1 : 0;
+    a.pool = (d.kind == RY_OP_CONV && k == 1 && d.level_idx == 1) ? 1 : 0;
+    if (a.pool && ((Hi | Wi) & 1)) RY_FAIL("conv: fused max-pool needs an even map");
     op.tmap_first = (int)maps.size();
     const size_t esz = 2;
     const cuuint64_t ctot = (cuuint64_t)tin.d.channels;
@@ -308,7 +311,11 @@ int bind_conv(ry_plan *p, Op &op, std::vector<CUtensorMap> &maps) {
         const cuuint64_t P = (cuuint64_t)B * Hi * Wi;
         a.tw = 128; a.th = 1; a.tn = 1;
         a.Wo = (int)P; a.Ho = 1; a.Bo = 1;
-        const cuuint32_t box[4] = {(cuuint32_t)cp.kb, 128, 1, 1};
+        if (a.pool) {                                  // 2-D pixel tiles (even extents) so that every 2x2 window lies in one tile
+            pick_tile(B, Hi, Wi, &a.tw, &a.th, &a.tn, true);
+            a.Wo = Wi; a.Ho = Hi; a.Bo = B;
+        }
+        const cuuint32_t box[4] = {(cuuint32_t)cp.kb, (cuuint32_t)a.tw, (cuuint32_t)a.th, (cuuint32_t)a.tn};
         a.n_src = cp.n_src;
         const ry_view *vs[3] = {&d.in0, &d.in1, &d.in2};
         int blk = 0;
@@ -316,8 +323,12 @@ int bind_conv(ry_plan *p, Op &op, std::vector<CUtensorMap> &maps) {
             const Tensor &ts = p->tensors[vs[si]->tensor];
             if (ts.h != Hi || ts.w != Wi) RY_FAIL("conv: concatenated inputs must share one pixel grid");
             const cuuint64_t cs = (cuuint64_t)ts.d.channels;
-            const cuuint64_t dims[4] = {(cuuint64_t)(cp.n_src > 1 ? vs[si]->c_len : d.cin), P, 1, 1};
-            const cuuint64_t str[3] = {cs * esz, P * cs * esz, P * cs * esz};
+            cuuint64_t dims[4] = {(cuuint64_t)(cp.n_src > 1 ? vs[si]->c_len : d.cin), P, 1, 1};
+            cuuint64_t str[3] = {cs * esz, P * cs * esz, P * cs * esz};
+            if (a.pool) {
+                dims[1] = (cuuint64_t)Wi; dims[2] = (cuuint64_t)Hi; dims[3] = (cuuint64_t)B;
+                str[1] = (cuuint64_t)Wi * cs * esz; str[2] = (cuuint64_t)Hi * Wi * cs * esz;
+            }
             if (encode_map(&m, bf(p, vs[si]->tensor) + vs[si]->c_off, 4, dims, str, box, cp.kb, vs[si]->c_len == ts.d.channels)) return 1;
             maps.push_back(m);
             if (cp.n_src > 1) {
@@ -407,7 +418,8 @@ int bind_conv(ry_plan *p, Op &op, std::vector<CUtensorMap> &maps) {
         return 0;
     }
     const Tensor &tout = p->tensors[d.out0.tensor];
-    if (tout.h != Ho || tout.w != Wo) RY_FAIL("conv: output tensor level does not match stride");
+    if (tout.h != (a.pool ? Ho / 2 : Ho) || tout.w != (a.pool ? Wo / 2 : Wo)) RY_FAIL("conv: output tensor level does not match stride");
+    if (a.pool && d.out1.tensor >= 0) RY_FAIL("conv: fused max-pool with a split store is not built");
     if (d.cout % 8 != 0) RY_FAIL("conv: cout must be a multiple of 8");
     OutPiece pieces[2];
     int n_pieces = 1;
@@ -445,7 +457,12 @@ int bind_conv(ry_plan *p, Op &op, std::vector<CUtensorMap> &maps) {
         const int ot = slot ? d.out1.tensor : d.out0.tensor;
         const cuuint64_t oc = (cuuint64_t)p->tensors[ot].d.channels;
         const cuuint64_t ce = n_pieces == 2 ? oc : c_end;
-        if (k == 1) {
+        if (a.pool) {
+            const cuuint64_t dims[4] = {ce, (cuuint64_t)(Wo / 2), (cuuint64_t)(Ho / 2), (cuuint64_t)B};
+            const cuuint64_t str[3] = {oc * esz, (cuuint64_t)(Wo / 2) * oc * esz, (cuuint64_t)(Ho / 2) * (Wo / 2) * oc * esz};
+            const cuuint32_t box[4] = {(cuuint32_t)wd, (cuuint32_t)(a.tw / 2), (cuuint32_t)(a.th / 2), (cuuint32_t)a.tn};
+            if (encode_map(&m, bf(p, ot), 4, dims, str, box, wd)) return 1;
+        } else if (k == 1) {
             const cuuint64_t P = (cuuint64_t)a.Wo;
             const cuuint64_t dims[4] = {ce, P, 1, 1};
             const cuuint64_t str[3] = {oc * esz, P * oc * esz, P * oc * esz};

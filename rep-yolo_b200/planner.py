@@ -86,19 +86,19 @@ class Plan:
         self.ops.append(d)
         return len(self.ops) - 1
 
-    def conv(self, layer, w, b, src, dst, stride=1, act=True, dst2=None, res=None, bvec=None):
+    def conv(self, layer, w, b, src, dst, stride=1, act=True, dst2=None, res=None, bvec=None, pool=False):
         cout, cin, k, _ = w.shape
         if isinstance(src, list):            # 1x1 conv over the channel concatenation of several views (no copy)
             assert k == 1 and res is None and bvec is None and 1 < len(src) <= 3 and sum(v[2] for v in src) == cin
             views = src + [None] * (3 - len(src))
             return self.op(N.OP_CONV, layer, in0=views[0], in1=views[1], in2=views[2], out0=dst, out1=dst2, ksize=1, stride=1,
                            act=N.ACT_SILU if act else N.ACT_NONE, cin=cin, cout=cout, n_src=len(src), w_off=self.blob.add(w),
-                           b_off=self.blob.add(b))
+                           b_off=self.blob.add(b), level_idx=1 if pool else 0)
         assert src[2] == cin, (layer, src, w.shape)
         assert (dst[2] + (dst2[2] if dst2 else 0)) == cout, (layer, dst, dst2, w.shape)
         return self.op(N.OP_CONV, layer, in0=src, in1=res, in2=bvec, out0=dst, out1=dst2, ksize=k, stride=stride,
                        act=N.ACT_SILU if act else N.ACT_NONE, cin=cin, cout=cout, w_off=self.blob.add(w),
-                       b_off=self.blob.add(b))
+                       b_off=self.blob.add(b), level_idx=1 if pool else 0)
 
 
     def chain(self, layer, src, main, posts):
@@ -139,6 +139,7 @@ def lower(layers, fz, nc=1, fuse_chains=None):
     import os
     if fuse_chains is None:
         fuse_chains = os.environ.get('RY_FUSE_CHAINS', '1') != '0'
+    fuse_pool = os.environ.get('RY_FUSE_POOL', '1') != '0'
     P = Plan()
     img = P.tensor(3, 0, N.RY_F32, N.T_EXTERNAL, N.X_IMAGE)
     pred = P.tensor(5 + nc, 0, N.RY_F32, N.T_EXTERNAL, N.X_PRED)
@@ -240,8 +241,20 @@ def lower(layers, fz, nc=1, fuse_chains=None):
                     P.conv(L.i, *W(f'{p}.cv{j}_1.conv'), src, h1)
                     P.conv(L.i, *W(f'{p}.stage{stage}.0.reparam_conv'), h1, h2)
                     P.conv(L.i, *W(f'{p}.cv{j}_2.conv'), h2, dstv)
-            dst = out_view(L, lvl)
-            P.conv(L.i, *W(f'{p}.cv1.conv'), [x1, x41, x43], dst)
+            nxt = layers[L.i + 1] if L.i + 1 < len(layers) else None
+            users = [M.i for M in layers if M.i > L.i and L.i in M.sources()]
+            if fuse_pool and nxt is not None and nxt.kind == 'MP' and users == [nxt.i]:
+                # MP (common.py:32-38) is the only consumer: its 2x2 max is fused into cv1's epilogue, the full-size map is never stored
+                skip.add(nxt.i)
+                g.layers.append(nxt.i)
+                g.out_layer = nxt.i
+                lvl += 1
+                dst = out_view(nxt, lvl)
+                P.conv(L.i, *W(f'{p}.cv1.conv'), [x1, x41, x43], dst, pool=True)
+                P.layer_out[nxt.i], levels[nxt.i] = dst, lvl
+            else:
+                dst = out_view(L, lvl)
+                P.conv(L.i, *W(f'{p}.cv1.conv'), [x1, x41, x43], dst)
         elif L.kind == 'MP':
             lvl = lvl_in + 1
             dst = out_view(L, lvl)

@@ -99,3 +99,44 @@ def test_multi_source_1x1_conv():
     got = arena_to_nchw(eng, dst)
     ref = F.silu(F.conv2d(torch.cat(xs, 1).bfloat16().float(), w.bfloat16().float(), b))
     assert float((got - ref).norm() / ref.norm()) < 4e-3
+
+
+@pytest.mark.parametrize('case', [
+    # sources, cout, image H, image W, pyramid level of the conv's map, B
+    ((48, 24, 48), 48, 128, 128, 1, 2),       # DER_Block L1 cv1 + MP: 64x64 map, tile teams
+    ((48, 24, 48), 128, 128, 128, 2, 2),      # L3: 32x32 map
+    ((128, 64, 128), 256, 320, 320, 3, 2),    # L5: 40x40 map, one N tile, tiles spanning two images
+    ((256, 128, 256), 512, 320, 320, 4, 3),   # L7: 20x20 map, two N tiles, odd batch
+    ((64,), 64, 96, 160, 2, 1),               # single source, non-square 24x40 map
+])
+def test_1x1_conv_with_fused_maxpool(case):
+    """DER_Block.cv1 with the following MP (common.py:32-38: MaxPool2d(2, 2)) fused in the epilogue: only the pooled map is stored."""
+    import repyolo_b200 as R
+    from gpu_util import planner, nchw_to_arena, arena_to_nchw
+    cs, cout, IH, IW, lvl, B = case
+    H, W = IH >> lvl, IW >> lvl
+    g = torch.Generator().manual_seed(sum(cs) + cout + H)
+    cin = sum(cs)
+    w = torch.randn(cout, cin, 1, 1, generator=g) / cin ** 0.5
+    b = torch.randn(cout, generator=g) * 0.5
+    xs = [torch.randn(B, c, H, W, generator=g) for c in cs]
+    P = planner.Plan()
+    tins = [P.full(P.tensor(c, lvl)) for c in cs]
+    tout = P.tensor(cout + 16, lvl + 1)
+    dst = (tout, 8, cout)
+    P.conv(0, w, b, tins if len(tins) > 1 else tins[0], dst, pool=True)
+    eng = R.NativeEngine(P, 1, 'cuda:0')
+    eng.bind(B, IH, IW)
+    eng.tensor(tout).fill_(7.0)
+    for v, x in zip(tins, xs):
+        nchw_to_arena(eng, v, x)
+    eng.run_ops(0, 1)
+    torch.cuda.synchronize()
+    got = arena_to_nchw(eng, dst)
+    ref = F.max_pool2d(F.silu(F.conv2d(torch.cat(xs, 1).bfloat16().float(), w.bfloat16().float(), b)), 2, 2)
+    assert got.shape == ref.shape
+    err = (got - ref).abs()
+    assert bool((err <= 2e-2 + 1e-2 * ref.abs()).all()), float(err.max())
+    assert float((got - ref).norm() / ref.norm()) < 4e-3
+    full = eng.tensor(tout).float().cpu()
+    assert bool((full[..., :8] == 7.0).all()) and bool((full[..., 8 + cout:] == 7.0).all())

@@ -179,6 +179,8 @@ def test_default_init_teacher_forced_1280_der_block():
     torch.cuda.synchronize()
     got = arena_to_nchw(eng, g.output)
     ref = O.run_fused_layer(fz, layers[1], x_in.bfloat16().float())
+    if g.out_layer == 2:                              # the MP that follows (L2) is fused into cv1's epilogue
+        ref = O.run_fused_layer(fz, layers[2], ref)
     assert rel_l2(got, ref) <= 3e-2
 
 
