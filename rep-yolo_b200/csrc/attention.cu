@@ -19,6 +19,8 @@
 // stay in fp32 registers; P and V enter the second product as bf16.
 #include "memops.cuh"
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace ry {
@@ -53,6 +55,84 @@ __global__ void __launch_bounds__(256) attn_qk_kernel(const __nv_bfloat16 *__res
     }
 }
 
+__device__ __forceinline__ float v_of(float x, float wv, float bv, float s1, float t1) {
+    return relu6_f(fmaf(s1, silu_f(fmaf(wv, x, bv)), t1));
+}
+
+// ---- operand preparation: one elementwise pass per attention module ----
+// For every pixel and channel group d (the 8 input channels of q/k output channel d = the 8 value channels 8d..8d+7):
+//   q = ReLU6(bn(SiLU(gconv_q(x)))), k likewise with the SAME bn (common.py:3693-3701), v = ReLU6(bn1(SiLU(wv*x + bv)))
+// written as the line kernels' shared-memory operand rows (bf16):
+//   QA[pix] = [Qhi | Qhi | Qlo | 0],  KB[pix] = [Khi | Klo | Khi | 0]   (KQ = 3*Cq padded to 16)   ->  QA.KB^T = Qhi.Khi + Qhi.Klo + Qlo.Khi
+//   V[pix]  = v[0..C)
+// so the row / column / energy / value passes stage their operands with plain 16-byte async copies.  A thread keeps the
+// constants of its group d in registers (blockDim % Cq == 0); q/k rows are assembled in shared memory and stored coalesced.
+constexpr int kPrepThreads = 256, kPrepUnroll = 4;
+
+__global__ void __launch_bounds__(kPrepThreads) attn_prep_kernel(const AttnParams p, int KQ, size_t npix, __nv_bfloat16 *__restrict__ QA,
+                                                                 __nv_bfloat16 *__restrict__ KB, __nv_bfloat16 *__restrict__ V) {
+    pdl_trigger();
+    extern __shared__ __align__(16) uint8_t prep_smem[];
+    const int Cq = p.Cq, C = p.C;
+    const int ppb = kPrepThreads / Cq;                                   // pixels per block iteration
+    __nv_bfloat16 *sQ = reinterpret_cast<__nv_bfloat16 *>(prep_smem), *sK = sQ + (size_t)kPrepUnroll * ppb * KQ;
+    const int d = threadIdx.x % Cq, pl = threadIdx.x / Cq;
+    const float *wq = p.qk, *bq = wq + Cq * 8, *wk = bq + Cq, *bk = wk + Cq * 8, *qs = bk + Cq, *qt = qs + Cq;
+    float rwq[8], rwk[8], rwv[8], rbv[8], rs1[8], rt1[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        rwq[j] = __ldg(wq + d * 8 + j); rwk[j] = __ldg(wk + d * 8 + j);
+        rwv[j] = __ldg(p.wv + d * 8 + j); rbv[j] = __ldg(p.bv + d * 8 + j);
+        rs1[j] = __ldg(p.s1 + d * 8 + j); rt1[j] = __ldg(p.t1 + d * 8 + j);
+    }
+    const float rbq = __ldg(bq + d), rbk = __ldg(bk + d), sc = __ldg(qs + d), sh = __ldg(qt + d);
+    for (int i = threadIdx.x; i < 2 * kPrepUnroll * ppb * KQ / 8; i += kPrepThreads) reinterpret_cast<uint4 *>(prep_smem)[i] = make_uint4(0, 0, 0, 0);   // K padding
+    pdl_wait();
+    __syncthreads();
+    const int rowv = KQ / 8;                                             // 16-byte vectors per operand row
+    const int rows_it = kPrepUnroll * ppb;                               // pixels per block iteration
+    for (size_t p0 = (size_t)blockIdx.x * rows_it; p0 < npix; p0 += (size_t)gridDim.x * rows_it) {
+        uint4 u[kPrepUnroll];
+#pragma unroll
+        for (int r = 0; r < kPrepUnroll; ++r) {                          // all loads in flight before the math
+            const size_t pix = p0 + pl + (size_t)r * ppb;
+            u[r] = pix < npix ? __ldg(reinterpret_cast<const uint4 *>(p.x + pix * p.x_cs + p.x_off + d * 8)) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int r = 0; r < kPrepUnroll; ++r) {
+            const size_t pix = p0 + pl + (size_t)r * ppb;
+            if (pix >= npix) continue;
+            const float2 f0 = unpack_bf16x2(u[r].x), f1 = unpack_bf16x2(u[r].y), f2 = unpack_bf16x2(u[r].z), f3 = unpack_bf16x2(u[r].w);
+            const float xv[8] = {f0.x, f0.y, f1.x, f1.y, f2.x, f2.y, f3.x, f3.y};
+            float aq = rbq, ak = rbk;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                aq = fmaf(rwq[j], xv[j], aq);
+                ak = fmaf(rwk[j], xv[j], ak);
+            }
+            const float qa = relu6_f(fmaf(sc, silu_f(aq), sh)), kb = relu6_f(fmaf(sc, silu_f(ak), sh));
+            uint32_t ow[4];
+#pragma unroll
+            for (int h = 0; h < 4; ++h)
+                ow[h] = pack_bf16x2(v_of(xv[2 * h], rwv[2 * h], rbv[2 * h], rs1[2 * h], rt1[2 * h]),
+                                    v_of(xv[2 * h + 1], rwv[2 * h + 1], rbv[2 * h + 1], rs1[2 * h + 1], rt1[2 * h + 1]));
+            *reinterpret_cast<uint4 *>(V + pix * C + d * 8) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+            const __nv_bfloat16 qh = __float2bfloat16_rn(qa), kh = __float2bfloat16_rn(kb);
+            const __nv_bfloat16 ql = __float2bfloat16_rn(qa - __bfloat162float(qh)), kl = __float2bfloat16_rn(kb - __bfloat162float(kh));
+            __nv_bfloat16 *ar = sQ + (size_t)(pl + r * ppb) * KQ, *br = sK + (size_t)(pl + r * ppb) * KQ;
+            ar[d] = qh; ar[Cq + d] = qh; ar[2 * Cq + d] = ql;
+            br[d] = kh; br[Cq + d] = kl; br[2 * Cq + d] = kh;
+        }
+        __syncthreads();
+        const int nrow = (int)min((size_t)rows_it, npix - p0);
+        for (int i = threadIdx.x; i < nrow * rowv; i += kPrepThreads) {
+            reinterpret_cast<uint4 *>(QA + p0 * KQ)[i] = reinterpret_cast<const uint4 *>(sQ)[i];
+            reinterpret_cast<uint4 *>(KB + p0 * KQ)[i] = reinterpret_cast<const uint4 *>(sK)[i];
+        }
+        __syncthreads();
+    }
+}
+
 // ---- warp-level tensor-core primitives ----
 __device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
@@ -70,20 +150,22 @@ __device__ __forceinline__ void mma_bf16(float *c, uint32_t a0, uint32_t a1, uin
                  : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, bool ok) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16 : 0) : "memory");   // !ok: zero fill
+}
 
 struct Geom {
     int L, LP, KQ;              // line length, padded to 16, padded 3*Cq contraction length
     int sq, sv, sp;             // row strides (elements) of Aq/Bk, Vs, Ps
 };
 
-__device__ __forceinline__ float v_of(float x, float wv, float bv, float s1, float t1) {
-    return relu6_f(fmaf(s1, silu_f(fmaf(wv, x, bv)), t1));
-}
 
 // LPC lines per CTA (short lines share a CTA for occupancy), one 16-row query tile per warp.  NT = LP / 8 (compile time:
 // register arrays).  Each line slot is an independent "virtual CTA" of NT*16 threads; only __syncthreads is shared.
 template <int MODE, int NT, int LPC>
-__global__ void __launch_bounds__(NT * 16 * LPC) attn_mma_kernel(const AttnParams p, const Geom gm, int total_lines, size_t slot_bytes) {
+__global__ void __launch_bounds__(NT * 16 * LPC) attn_mma_kernel(const AttnParams p, const Geom gm, int total_lines, size_t slot_bytes,
+                                                                 const __nv_bfloat16 *__restrict__ qa, const __nv_bfloat16 *__restrict__ kb,
+                                                                 const __nv_bfloat16 *__restrict__ vv) {
     pdl_trigger();
     pdl_wait();
     extern __shared__ __align__(16) uint8_t sm_all[];
@@ -93,7 +175,7 @@ __global__ void __launch_bounds__(NT * 16 * LPC) attn_mma_kernel(const AttnParam
     const int vb = blockIdx.x * LPC + slot;                  // global line index
     const bool active = vb < total_lines;
     uint8_t *sm_raw = sm_all + (size_t)slot * slot_bytes;
-    const int L = gm.L, C = p.C, Cq = p.Cq, KQ = gm.KQ;
+    const int L = gm.L, C = p.C, KQ = gm.KQ;
     const int sq = gm.sq, sv = gm.sv, sp = gm.sp;
     __nv_bfloat16 *Aq = reinterpret_cast<__nv_bfloat16 *>(sm_raw);
     __nv_bfloat16 *Bk = Aq + (size_t)LP * sq;
@@ -102,81 +184,34 @@ __global__ void __launch_bounds__(NT * 16 * LPC) attn_mma_kernel(const AttnParam
     const int lines = (MODE == MODE_ROW) ? p.H : p.W;
     const int b = (active ? vb : 0) / lines, line = (active ? vb : 0) % lines;
     const size_t img = (size_t)b * p.H * p.W;
+    float *row_stats = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(p.scratch) + (((size_t)p.B * p.H * p.W * p.C * 2 + 255) & ~size_t(255)));
     const int warp = tis >> 5, lane = tis & 31;
     const int g = lane >> 2, t4 = lane & 3;
     auto pix_of = [&](int i) -> size_t {       // pixel of line position i
         return (MODE == MODE_ROW) ? img + (size_t)line * p.W + i : img + (size_t)i * p.W + line;
     };
 
-    // ---- stage operands ----
-    if (MODE != MODE_VPV && active) {
-        // Aq row = [Qhi | Qhi | Qlo | 0], Bk row = [Khi | Klo | Khi | 0]  ->  Aq.Bk^T = Qhi.Khi + Qhi.Klo + Qlo.Khi
-        // q = ReLU6(bn(SiLU(gconv_q(x)))), k likewise with the SAME bn (common.py:3693-3701), computed here from the 8 input
-        // channels of group d -- the same 16 bytes of x that give the 8 value channels v[8d..8d+7] (no q/k round trip through HBM)
-        const __nv_bfloat16 zero = __float2bfloat16_rn(0.0f);
-        const float *wq = p.qk, *bq = wq + Cq * 8, *wk = bq + Cq, *bk = wk + Cq * 8, *qs = bk + Cq, *qt = qs + Cq;
-        for (int idx = tis; idx < LP * Cq; idx += kThreads) {
-            const int pi = idx / Cq, d = idx - pi * Cq;
-            float qa = 0.0f, kb = 0.0f;
-            uint4 vo = make_uint4(0, 0, 0, 0);
-            if (pi < L) {
-                const uint4 u = __ldg(reinterpret_cast<const uint4 *>(p.x + pix_of(pi) * p.x_cs + p.x_off + d * 8));
-                const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
-                const float xv[8] = {f0.x, f0.y, f1.x, f1.y, f2.x, f2.y, f3.x, f3.y};
-                float aq = __ldg(bq + d), ak = __ldg(bk + d);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    aq = fmaf(__ldg(wq + d * 8 + j), xv[j], aq);
-                    ak = fmaf(__ldg(wk + d * 8 + j), xv[j], ak);
-                }
-                const float sc = __ldg(qs + d), sh = __ldg(qt + d);
-                qa = relu6_f(fmaf(sc, silu_f(aq), sh));
-                kb = relu6_f(fmaf(sc, silu_f(ak), sh));
-                if (MODE != MODE_VE) {
-                    uint32_t ow[4];
-#pragma unroll
-                    for (int h = 0; h < 4; ++h) {
-                        const int c0 = d * 8 + 2 * h;
-                        ow[h] = pack_bf16x2(v_of(xv[2 * h], __ldg(p.wv + c0), __ldg(p.bv + c0), __ldg(p.s1 + c0), __ldg(p.t1 + c0)),
-                                            v_of(xv[2 * h + 1], __ldg(p.wv + c0 + 1), __ldg(p.bv + c0 + 1), __ldg(p.s1 + c0 + 1),
-                                                 __ldg(p.t1 + c0 + 1)));
-                    }
-                    vo = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-                }
+    // ---- stage operands: async 16-byte copies of the prepared rows (rows >= L are zero filled) ----
+    if (active) {
+        const uint32_t aq_u = smem_addr(Aq), bk_u = smem_addr(Bk), vs_u = smem_addr(Vs);
+        if (MODE != MODE_VPV) {
+            const int rowv = KQ / 8;
+            for (int idx = tis; idx < LP * rowv; idx += kThreads) {
+                const int pi = idx / rowv, c = idx - pi * rowv;
+                const bool ok = pi < L;
+                const size_t px = ok ? pix_of(pi) : 0;
+                cp_async16(aq_u + (uint32_t)(pi * sq + c * 8) * 2, qa + px * KQ + c * 8, ok);
+                cp_async16(bk_u + (uint32_t)(pi * sq + c * 8) * 2, kb + px * KQ + c * 8, ok);
             }
-            const __nv_bfloat16 qh = __float2bfloat16_rn(qa), kh = __float2bfloat16_rn(kb);
-            const __nv_bfloat16 ql = __float2bfloat16_rn(qa - __bfloat162float(qh)), kl = __float2bfloat16_rn(kb - __bfloat162float(kh));
-            __nv_bfloat16 *ar = Aq + (size_t)pi * sq, *br = Bk + (size_t)pi * sq;
-            ar[d] = qh; ar[Cq + d] = qh; ar[2 * Cq + d] = ql;
-            br[d] = kh; br[Cq + d] = kl; br[2 * Cq + d] = kh;
-            if (MODE != MODE_VE) *reinterpret_cast<uint4 *>(Vs + (size_t)pi * sv + d * 8) = vo;
         }
-        const int padc = KQ - 3 * Cq;
-        for (int idx = tis; idx < LP * padc; idx += kThreads) {
-            const int pi = idx / padc, col = 3 * Cq + idx - pi * padc;
-            Aq[(size_t)pi * sq + col] = zero;
-            Bk[(size_t)pi * sq + col] = zero;
-        }
-    }
-    if (MODE == MODE_VPV && active) {
-        const int vecs = C / 8;
-        for (int idx = tis; idx < LP * vecs; idx += kThreads) {
-            const int pi = idx / vecs, c = (idx - pi * vecs) * 8;
-            uint4 o = make_uint4(0, 0, 0, 0);
-            if (pi < L) {
-                const uint4 u = __ldg(reinterpret_cast<const uint4 *>(p.x + pix_of(pi) * p.x_cs + p.x_off + c));
-                const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
-                uint32_t ow[4];
-#pragma unroll
-                for (int h = 0; h < 4; ++h) {
-                    const float2 f = unpack_bf16x2(uw[h]);
-                    const int c0 = c + 2 * h;
-                    ow[h] = pack_bf16x2(v_of(f.x, __ldg(p.wv + c0), __ldg(p.bv + c0), __ldg(p.s1 + c0), __ldg(p.t1 + c0)),
-                                        v_of(f.y, __ldg(p.wv + c0 + 1), __ldg(p.bv + c0 + 1), __ldg(p.s1 + c0 + 1), __ldg(p.t1 + c0 + 1)));
-                }
-                o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+        if (MODE != MODE_VE) {
+            const int vecs = C / 8;
+            for (int idx = tis; idx < LP * vecs; idx += kThreads) {
+                const int pi = idx / vecs, c = idx - pi * vecs;
+                const bool ok = pi < L;
+                const size_t px = ok ? pix_of(pi) : 0;
+                cp_async16(vs_u + (uint32_t)(pi * sv + c * 8) * 2, vv + px * C + c * 8, ok);
             }
-            *reinterpret_cast<uint4 *>(Vs + (size_t)pi * sv + c) = o;
         }
     }
     if (MODE == MODE_VPV && active) {
@@ -185,13 +220,14 @@ __global__ void __launch_bounds__(NT * 16 * LPC) attn_mma_kernel(const AttnParam
         // flat pixels n'*H .. n'*H + H-1 (row-major) -- for H == W that is image row n'
         const __nv_bfloat16 *E = reinterpret_cast<const __nv_bfloat16 *>(p.scratch) + ((size_t)b * p.H * p.W + (size_t)line * p.H) * LP;
         const int vecs = LP / 8;
+        const uint32_t ps_u = smem_addr(Ps);
         for (int idx = tis; idx < LP * vecs; idx += kThreads) {
             const int j = idx / vecs, c = (idx - j * vecs) * 8;
-            uint4 o = make_uint4(0, 0, 0, 0);
-            if (j < L) o = __ldg(reinterpret_cast<const uint4 *>(E + (size_t)j * LP + c));
-            *reinterpret_cast<uint4 *>(Ps + (size_t)j * sp + c) = o;
+            cp_async16(ps_u + (uint32_t)(j * sp + c) * 2, E + (size_t)(j < L ? j : 0) * LP + c, j < L);
         }
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
     if (!active) return;
 
@@ -284,16 +320,17 @@ __global__ void __launch_bounds__(NT * 16 * LPC) attn_mma_kernel(const AttnParam
             if (i >= L) continue;
             const size_t px = pix_of(i);
             if (MODE == MODE_ROW) {
-                float *sc = p.scratch + px * (C + 4);
+                // un-normalised row partial O_W as bf16 [pix][C] (it re-enters a bf16 result scaled by gamma), statistics fp32 [pix][2]
+                uint32_t *sc = reinterpret_cast<uint32_t *>(reinterpret_cast<__nv_bfloat16 *>(p.scratch) + px * C + c0 + 2 * t4);
 #pragma unroll
-                for (int ct = 0; ct < 4; ++ct)
-                    *reinterpret_cast<float2 *>(sc + c0 + ct * 8 + 2 * t4) = make_float2(o[ct][2 * hh], o[ct][2 * hh + 1]);
-                if (c0 == 0 && t4 == 0) { sc[C] = m_row[hh]; sc[C + 1] = s_row[hh]; }
+                for (int ct = 0; ct < 4; ++ct) sc[ct * 4] = pack_bf16x2(o[ct][2 * hh], o[ct][2 * hh + 1]);
+                if (c0 == 0 && t4 == 0) *reinterpret_cast<float2 *>(row_stats + px * 2) = make_float2(m_row[hh], s_row[hh]);
             } else {
                 float fh = 1.0f, fw = 0.0f, inv = 1.0f;
-                const float *sc = p.scratch + px * (C + 4);
+                const __nv_bfloat16 *sc = reinterpret_cast<const __nv_bfloat16 *>(p.scratch) + px * C;
                 if (MODE == MODE_COL) {
-                    const float mw = sc[C], sw = sc[C + 1], mh = m_row[hh], sh = s_row[hh];
+                    const float2 ms = *reinterpret_cast<const float2 *>(row_stats + px * 2);
+                    const float mw = ms.x, sw = ms.y, mh = m_row[hh], sh = s_row[hh];
                     const float m = fmaxf(mh, mw);
                     fh = __expf(mh - m);
                     fw = __expf(mw - m);
@@ -304,7 +341,7 @@ __global__ void __launch_bounds__(NT * 16 * LPC) attn_mma_kernel(const AttnParam
                     const int c = c0 + ct * 8 + 2 * t4;
                     float o0 = o[ct][2 * hh], o1 = o[ct][2 * hh + 1];
                     if (MODE == MODE_COL) {
-                        const float2 ow = *reinterpret_cast<const float2 *>(sc + c);
+                        const float2 ow = unpack_bf16x2(*reinterpret_cast<const uint32_t *>(sc + c));
                         o0 = (o0 * fh + ow.x * fw) * inv;
                         o1 = (o1 * fh + ow.y * fw) * inv;
                     }
@@ -321,6 +358,33 @@ int pick_nt(int L) {
     static const int opts[] = {2, 4, 6, 8, 10, 12, 16, 20};
     for (int nt : opts)
         if (nt * 8 >= L) return nt;
+    return 0;
+}
+
+size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+size_t pass_scratch_bytes(int B, int H, int W, int C);
+
+struct PrepBufs { __nv_bfloat16 *qa, *kb, *v; int KQ; };
+// scratch = [row partials / energies | QA | KB | V]
+PrepBufs prep_bufs(const AttnParams &p) {
+    PrepBufs b;
+    b.KQ = (3 * p.Cq + 15) / 16 * 16;
+    const size_t npix = (size_t)p.B * p.H * p.W;
+    uint8_t *base = reinterpret_cast<uint8_t *>(p.scratch) + align256(pass_scratch_bytes(p.B, p.H, p.W, p.C));
+    b.qa = reinterpret_cast<__nv_bfloat16 *>(base);
+    b.kb = reinterpret_cast<__nv_bfloat16 *>(base + align256(npix * b.KQ * 2));
+    b.v = reinterpret_cast<__nv_bfloat16 *>(base + 2 * align256(npix * b.KQ * 2));
+    return b;
+}
+
+int prep_launch(const AttnParams &p, cudaStream_t st) {
+    if (kPrepThreads % p.Cq != 0 || p.C != p.Cq * 8) return 1;
+    const PrepBufs pb = prep_bufs(p);
+    const size_t npix = (size_t)p.B * p.H * p.W;
+    const int ppb = kPrepUnroll * kPrepThreads / p.Cq;
+    const size_t blocks = (npix + ppb - 1) / ppb;
+    const int grid = (int)std::min<size_t>(blocks, (size_t)kNumSMs * 8);
+    launch_pdl(attn_prep_kernel, dim3(grid), dim3(kPrepThreads), (size_t)2 * ppb * pb.KQ * 2, st, p, pb.KQ, npix, pb.qa, pb.kb, pb.v);
     return 0;
 }
 
@@ -346,7 +410,9 @@ int launch_nt(const AttnParams &p, int L, cudaStream_t st) {
     }
     const int lines = (MODE == MODE_ROW) ? p.H : p.W;
     const int total = p.B * lines;
-    launch_pdl(attn_mma_kernel<MODE, NT, LPC>, dim3((total + LPC - 1) / LPC), dim3(NT * 16 * LPC), smem * LPC, st, p, gm, total, smem);
+    const PrepBufs pb = prep_bufs(p);
+    launch_pdl(attn_mma_kernel<MODE, NT, LPC>, dim3((total + LPC - 1) / LPC), dim3(NT * 16 * LPC), smem * LPC, st, p, gm, total, smem,
+               (const __nv_bfloat16 *)pb.qa, (const __nv_bfloat16 *)pb.kb, (const __nv_bfloat16 *)pb.v);
     return 0;
 }
 
@@ -379,19 +445,30 @@ void attn_qk_launch(const __nv_bfloat16 *x, int x_cs, int x_off, int C, int Cq, 
     launch_pdl(attn_qk_kernel, dim3((int)g), dim3(256), 0, st, x, x_cs, x_off, Cq, npix, wq, bq, wk, bk, s, t, q, k);
 }
 
-// crisscross: [B*H*W][C + 4] fp32 row-pass partials; vertical: [B][H][W][LP] bf16 energies -- one shared region
-size_t attn_scratch_bytes(int B, int H, int W, int C) {
-    const size_t cc = (size_t)B * H * W * (C + 4) * 4;
+// crisscross: [B*H*W][C] bf16 row-pass partials + [B*H*W][2] fp32 statistics; vertical: [B][H][W][LP] bf16 energies -- one
+// shared region, followed by the prepared operands QA | KB | V
+namespace {
+size_t pass_scratch_bytes(int B, int H, int W, int C) {
+    const size_t cc = align256((size_t)B * H * W * C * 2) + (size_t)B * H * W * 8;   // bf16 row partials + fp32 (max, sum)
     const size_t ve = (size_t)B * H * W * (size_t)(pick_nt(H) * 8) * 2;
     return cc > ve ? cc : ve;
 }
+}  // namespace
+
+size_t attn_scratch_bytes(int B, int H, int W, int C) {
+    const size_t npix = (size_t)B * H * W;
+    const int KQ = (3 * (C / 8) + 15) / 16 * 16;
+    return align256(pass_scratch_bytes(B, H, W, C)) + 2 * align256(npix * KQ * 2) + align256(npix * C * 2);
+}
 
 int crisscross_launch(const AttnParams &p, cudaStream_t st) {
+    if (prep_launch(p, st)) return 1;
     if (launch_mode<MODE_ROW>(p, st)) return 1;
     return launch_mode<MODE_COL>(p, st);
 }
 
 int vertical_launch(const AttnParams &p, cudaStream_t st) {
+    if (prep_launch(p, st)) return 1;
     if (launch_mode<MODE_VE>(p, st)) return 1;
     return launch_mode<MODE_VPV>(p, st);
 }

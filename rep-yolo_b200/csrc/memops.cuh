@@ -32,13 +32,13 @@ struct AttnParams {
     float gamma;
     __nv_bfloat16 *out;       // output map view
     int out_cs, out_off;
-    float *scratch;           // criss-cross: row-pass partials [B*H*W, C + 4] fp32; vertical: energies [B,H,W,LP] bf16
+    float *scratch;           // criss-cross: row partials [B*H*W, C] bf16 + (max, sum) fp32; vertical: energies [B,H,W,LP] bf16; then QA | KB | V
 };
 void attn_qk_launch(const __nv_bfloat16 *x, int x_cs, int x_off, int C, int Cq, size_t npix, const float *wq,
                     const float *bq, const float *wk, const float *bk, const float *s, const float *t, float *q, float *k,
                     cudaStream_t st);
 int crisscross_launch(const AttnParams &p, cudaStream_t st);
 int vertical_launch(const AttnParams &p, cudaStream_t st);
-size_t attn_scratch_bytes(int B, int H, int W, int C);   // shared by crisscross (fp32 row partials) and vertical (bf16 energies)
+size_t attn_scratch_bytes(int B, int H, int W, int C);   // row partials / energies + prepared operands QA, KB, V
 
 }  // namespace ry
