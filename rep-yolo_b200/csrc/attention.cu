@@ -28,6 +28,8 @@ namespace ry {
 namespace {
 
 enum { MODE_ROW = 0, MODE_COL = 1, MODE_VE = 2, MODE_VPV = 3 };
+constexpr int kStagePitch = 40;                               // epilogue staging row: 32 channels + 8 pad (bf16)
+constexpr int kStageElems = 16 * kStagePitch + 32;            // per warp: 16 rows + 16 fp32 row weights
 
 __global__ void __launch_bounds__(256) attn_qk_kernel(const __nv_bfloat16 *__restrict__ x, int x_cs, int x_off, int Cq,
                                                       size_t npix, const float *__restrict__ wq, const float *__restrict__ bq,
@@ -229,11 +231,10 @@ __global__ void __launch_bounds__(NT * 16 * LPC) attn_mma_kernel(const AttnParam
     asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
-    if (!active) return;
 
     const int row0 = warp * 16;                                  // this warp's query rows
     float m_row[2] = {0.0f, 0.0f}, s_row[2] = {1.0f, 1.0f};
-    if (MODE != MODE_VPV) {
+    if (MODE != MODE_VPV && active) {
         // ---- E = Aq . Bk^T for rows row0..row0+15, all LP columns ----
         float e[NT][4];
 #pragma unroll
@@ -294,8 +295,39 @@ __global__ void __launch_bounds__(NT * 16 * LPC) attn_mma_kernel(const AttnParam
         }
         __syncwarp();
     }
+    if (MODE == MODE_VE) return;
+    if (MODE != MODE_VPV) __syncthreads();                       // every warp is done with Aq / Bk: the region becomes the epilogue staging
+    if (!active) return;
 
-    // ---- O = P . V in chunks of 32 channels; epilogue per chunk ----
+    // ---- O = P . V in chunks of 32 channels.  Epilogue per chunk through a per-warp staging tile (16 rows x 32 channels bf16,
+    //      in the dead Aq/Bk region; the value pass has its own) so that every global access is a 16-byte vector of one pixel ----
+    __nv_bfloat16 *wst = ((MODE == MODE_VPV) ? Ps + (size_t)LP * sp : Aq) + (size_t)warp * kStageElems;
+    float *wsc = reinterpret_cast<float *>(wst + 16 * kStagePitch);                       // [16] per-row weight of the row partial
+    float a_h[2] = {1.0f, 1.0f};
+    if (MODE == MODE_COL) {
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+            const int i = row0 + g + 8 * hh;
+            float aw = 0.0f;
+            if (i < L) {
+                const float2 ms = *reinterpret_cast<const float2 *>(row_stats + pix_of(i) * 2);
+                const float mw = ms.x, sw = ms.y, mh = m_row[hh], sh = s_row[hh];
+                const float m = fmaxf(mh, mw);
+                const float fh = __expf(mh - m), fw = __expf(mw - m);
+                const float inv = 1.0f / (sh * fh + sw * fw);
+                a_h[hh] = fh * inv;
+                aw = fw * inv;
+            }
+            if (t4 == 0) wsc[g + 8 * hh] = aw;
+        }
+    }
+    if (MODE == MODE_ROW && t4 == 0) {
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+            const int i = row0 + g + 8 * hh;
+            if (i < L) *reinterpret_cast<float2 *>(row_stats + pix_of(i) * 2) = make_float2(m_row[hh], s_row[hh]);
+        }
+    }
     const uint32_t pa_base = smem_addr(Ps + (size_t)(row0 + (lane & 15)) * sp + (lane >> 4) * 8);
     const uint32_t vb_base = smem_addr(Vs + (size_t)((lane & 7) + ((lane >> 3) & 1) * 8) * sv + (lane >> 4) * 8);
     for (int c0 = 0; c0 < C; c0 += 32) {
@@ -314,41 +346,41 @@ __global__ void __launch_bounds__(NT * 16 * LPC) attn_mma_kernel(const AttnParam
                 mma_bf16(o[2 * cp + 1], a0, a1, a2, a3, b2, b3);
             }
         }
+        __syncwarp();                                            // previous chunk's staging reads are done
 #pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-            const int i = row0 + g + 8 * hh;
+        for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+            for (int ct = 0; ct < 4; ++ct)
+                *reinterpret_cast<uint32_t *>(wst + (g + 8 * hh) * kStagePitch + ct * 8 + 2 * t4) =
+                    pack_bf16x2(o[ct][2 * hh] * a_h[hh], o[ct][2 * hh + 1] * a_h[hh]);
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int idx = lane + 32 * k, r = idx >> 2, v = idx & 3;
+            const int i = row0 + r;
             if (i >= L) continue;
             const size_t px = pix_of(i);
+            const uint4 oh = *reinterpret_cast<const uint4 *>(wst + r * kStagePitch + v * 8);
+            const int c = c0 + v * 8;
             if (MODE == MODE_ROW) {
-                // un-normalised row partial O_W as bf16 [pix][C] (it re-enters a bf16 result scaled by gamma), statistics fp32 [pix][2]
-                uint32_t *sc = reinterpret_cast<uint32_t *>(reinterpret_cast<__nv_bfloat16 *>(p.scratch) + px * C + c0 + 2 * t4);
-#pragma unroll
-                for (int ct = 0; ct < 4; ++ct) sc[ct * 4] = pack_bf16x2(o[ct][2 * hh], o[ct][2 * hh + 1]);
-                if (c0 == 0 && t4 == 0) *reinterpret_cast<float2 *>(row_stats + px * 2) = make_float2(m_row[hh], s_row[hh]);
+                // un-normalised row partial O_W as bf16 [pix][C] (it re-enters a bf16 result scaled by gamma)
+                *reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(p.scratch) + px * C + c) = oh;
             } else {
-                float fh = 1.0f, fw = 0.0f, inv = 1.0f;
-                const __nv_bfloat16 *sc = reinterpret_cast<const __nv_bfloat16 *>(p.scratch) + px * C;
+                const uint4 xw = __ldg(reinterpret_cast<const uint4 *>(p.x + px * p.x_cs + p.x_off + c));
+                uint4 pw = make_uint4(0, 0, 0, 0);
+                float aw = 0.0f;
                 if (MODE == MODE_COL) {
-                    const float2 ms = *reinterpret_cast<const float2 *>(row_stats + px * 2);
-                    const float mw = ms.x, sw = ms.y, mh = m_row[hh], sh = s_row[hh];
-                    const float m = fmaxf(mh, mw);
-                    fh = __expf(mh - m);
-                    fw = __expf(mw - m);
-                    inv = 1.0f / (sh * fh + sw * fw);
+                    pw = *reinterpret_cast<const uint4 *>(reinterpret_cast<const __nv_bfloat16 *>(p.scratch) + px * C + c);
+                    aw = wsc[r];
                 }
+                const uint32_t ohw[4] = {oh.x, oh.y, oh.z, oh.w}, xww[4] = {xw.x, xw.y, xw.z, xw.w}, pww[4] = {pw.x, pw.y, pw.z, pw.w};
+                uint32_t res[4];
 #pragma unroll
-                for (int ct = 0; ct < 4; ++ct) {
-                    const int c = c0 + ct * 8 + 2 * t4;
-                    float o0 = o[ct][2 * hh], o1 = o[ct][2 * hh + 1];
-                    if (MODE == MODE_COL) {
-                        const float2 ow = unpack_bf16x2(*reinterpret_cast<const uint32_t *>(sc + c));
-                        o0 = (o0 * fh + ow.x * fw) * inv;
-                        o1 = (o1 * fh + ow.y * fw) * inv;
-                    }
-                    const float2 xv = unpack_bf16x2(__ldg(reinterpret_cast<const uint32_t *>(p.x + px * p.x_cs + p.x_off + c)));
-                    *reinterpret_cast<uint32_t *>(p.out + px * p.out_cs + p.out_off + c) =
-                        pack_bf16x2(fmaf(p.gamma, o0, xv.x), fmaf(p.gamma, o1, xv.y));
+                for (int q = 0; q < 4; ++q) {
+                    const float2 fo = unpack_bf16x2(ohw[q]), fx = unpack_bf16x2(xww[q]), fp = unpack_bf16x2(pww[q]);
+                    res[q] = pack_bf16x2(fmaf(p.gamma, fmaf(fp.x, aw, fo.x), fx.x), fmaf(p.gamma, fmaf(fp.y, aw, fo.y), fx.y));
                 }
+                *reinterpret_cast<uint4 *>(p.out + px * p.out_cs + p.out_off + c) = make_uint4(res[0], res[1], res[2], res[3]);
             }
         }
     }
@@ -401,6 +433,8 @@ int launch_nt(const AttnParams &p, int L, cudaStream_t st) {
     size_t smem = 0;
     if (MODE != MODE_VPV) smem += 2 * (size_t)gm.LP * gm.sq * 2;
     if (MODE != MODE_VE) smem += (size_t)gm.LP * gm.sv * 2 + (size_t)gm.LP * gm.sp * 2;
+    if (MODE == MODE_VPV) smem += (size_t)(NT / 2) * kStageElems * 2;          // row / column passes stage in the dead q/k operand region
+    if (MODE == MODE_ROW || MODE == MODE_COL) smem = std::max(smem, (size_t)(NT / 2) * kStageElems * 2);
     smem = (smem + 15) & ~size_t(15);
     if (smem * LPC > 227 * 1024) return 1;
     static bool attr_set = false;
