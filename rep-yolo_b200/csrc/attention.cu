@@ -415,7 +415,7 @@ int prep_launch(const AttnParams &p, cudaStream_t st) {
     const size_t npix = (size_t)p.B * p.H * p.W;
     const int ppb = kPrepUnroll * kPrepThreads / p.Cq;
     const size_t blocks = (npix + ppb - 1) / ppb;
-    const int grid = (int)std::min<size_t>(blocks, (size_t)kNumSMs * 8);
+    const int grid = (int)std::min<size_t>(blocks, (size_t)kNumSMs * 2);   // resident CTAs: the per-group constants are fetched once
     launch_pdl(attn_prep_kernel, dim3(grid), dim3(kPrepThreads), (size_t)2 * ppb * pb.KQ * 2, st, p, pb.KQ, npix, pb.qa, pb.kb, pb.v);
     return 0;
 }

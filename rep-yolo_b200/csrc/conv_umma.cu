@@ -35,19 +35,49 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+__device__ __forceinline__ float ld_shared_f(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
 __device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
     return v;
 }
 
+// Residual / per-image vector operands of one 16-column epilogue step, fetched one step AHEAD of their use (the loads are
+// L1/L2-latency bound; issued back to back they overlap the TMEM load and the math of the previous step).
+struct EpiExtra {
+    uint4 r[2];      // residual: 2 x 8 bf16
+    float4 v[4];     // per-image vector: 16 fp32
+};
+
+// EXTRA: bit 0 = residual, bit 1 = per-image vector (compile time, so the unused operand costs no registers)
+template <int EXTRA>
+__device__ __forceinline__ void epi_fetch(const ConvArgs &p, EpiExtra &x, bool valid, size_t pix, int img, int ch, int halves) {
+    if (!EXTRA) return;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        if (EXTRA & 1) x.r[j] = make_uint4(0, 0, 0, 0);
+        if (EXTRA & 2) x.v[2 * j] = x.v[2 * j + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid && j < halves) {
+            if (EXTRA & 1) x.r[j] = __ldg(reinterpret_cast<const uint4 *>(p.res + pix * p.res_cs + p.res_off + ch + 8 * j));
+            if (EXTRA & 2) {
+                const float4 *bv = reinterpret_cast<const float4 *>(p.bvec + (size_t)img * p.bvec_cs + p.bvec_off + ch + 8 * j);
+                x.v[2 * j] = __ldg(bv);
+                x.v[2 * j + 1] = __ldg(bv + 1);
+            }
+        }
+    }
+}
+
 // 8 accumulator columns -> bias, activation, optional residual / per-image vector -> 8 bf16 (one 16-byte chunk).
 //   t = acc*scale + sbias (sbias is pre-multiplied by scale: 0.5 for SiLU, 1 for identity)
 //   SiLU(x) = x*sigmoid(x) = h + h*tanh(h), h = x/2   (one MUFU.TANH instead of EX2 + RCP)
 // EXTRA = false compiles the residual / broadcast-add paths out (predicated-off instructions still cost issue slots).
-template <bool EXTRA>
-__device__ __forceinline__ uint4 epi_chunk8(const ConvArgs &p, const uint32_t *raw, uint32_t sb_addr, float scale, bool act,
-                                           bool valid, size_t pix, int img, int ch) {
+template <int EXTRA>
+__device__ __forceinline__ uint4 epi_chunk8(const uint32_t *raw, uint32_t sb_addr, float scale, bool act, const EpiExtra &ex, int j) {
     float x[8];
     const float4 b0 = ld_shared_f4(sb_addr), b1 = ld_shared_f4(sb_addr + 16);
     const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
@@ -57,48 +87,31 @@ __device__ __forceinline__ uint4 epi_chunk8(const ConvArgs &p, const uint32_t *r
 #pragma unroll
         for (int i = 0; i < 8; ++i) x[i] = fmaf(x[i], ptx::tanh_approx(x[i]), x[i]);
     }
-    if (EXTRA) {
-        if (p.res != nullptr && valid) {
-            const uint4 r = __ldg(reinterpret_cast<const uint4 *>(p.res + pix * p.res_cs + p.res_off + ch));
-            const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
+    if (EXTRA & 1) {
+        const uint32_t rw[4] = {ex.r[j].x, ex.r[j].y, ex.r[j].z, ex.r[j].w};
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float2 f = unpack_bf16x2(rw[i]);
-                x[2 * i] += f.x;
-                x[2 * i + 1] += f.y;
-            }
+        for (int i = 0; i < 4; ++i) {
+            const float2 f = unpack_bf16x2(rw[i]);
+            x[2 * i] += f.x;
+            x[2 * i + 1] += f.y;
         }
-        if (p.bvec != nullptr && valid) {
-            const float4 *bv = reinterpret_cast<const float4 *>(p.bvec + (size_t)img * p.bvec_cs + p.bvec_off + ch);
-            const float4 v0 = __ldg(bv), v1 = __ldg(bv + 1);
-            x[0] += v0.x; x[1] += v0.y; x[2] += v0.z; x[3] += v0.w;
-            x[4] += v1.x; x[5] += v1.y; x[6] += v1.z; x[7] += v1.w;
-        }
+    }
+    if (EXTRA & 2) {
+        const float4 v0 = ex.v[2 * j], v1 = ex.v[2 * j + 1];
+        x[0] += v0.x; x[1] += v0.y; x[2] += v0.z; x[3] += v0.w;
+        x[4] += v1.x; x[5] += v1.y; x[6] += v1.z; x[7] += v1.w;
     }
     return make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]), pack_bf16x2(x[6], x[7]));
 }
 
 // IDetect.fuseforward decode (reference models/yolo.py:139-156): same op order, fp32.
-__device__ __forceinline__ void detect_epilogue(const ConvArgs &p, const uint32_t *raw, int j0, size_t pix) {
-    const int b = (int)(pix / p.img_hw);
-    const int rem = (int)(pix - (size_t)b * p.img_hw);
-    const int gy = rem / p.img_w, gx = rem - gy * p.img_w;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        const int j = j0 + i;
-        if (j >= p.na * p.no) break;
-        const int a = j / p.no, o = j - a * p.no;
-        const float t = __uint_as_float(raw[i]) + __ldg(p.bias + j);
-        if (p.raw != nullptr) p.raw[(((size_t)b * p.na + a) * p.img_hw + rem) * p.no + o] = t;
-        const float s = 1.0f / (1.0f + expf(-t));
-        float y;
-        if (o == 0) y = (s * 2.0f - 0.5f + (float)gx) * p.det_stride;
-        else if (o == 1) y = (s * 2.0f - 0.5f + (float)gy) * p.det_stride;
-        else if (o == 2) { const float u = s * 2.0f; y = u * u * p.anchors[2 * a]; }
-        else if (o == 3) { const float u = s * 2.0f; y = u * u * p.anchors[2 * a + 1]; }
-        else y = s;
-        p.pred[((size_t)b * p.rows_total + p.row_off + (size_t)a * p.img_hw + rem) * p.no + o] = y;
-    }
+__device__ __forceinline__ float detect_decode(const ConvArgs &p, float t, int a, int o, int gx, int gy) {
+    const float s = 1.0f / (1.0f + expf(-t));
+    if (o == 0) return (s * 2.0f - 0.5f + (float)gx) * p.det_stride;
+    if (o == 1) return (s * 2.0f - 0.5f + (float)gy) * p.det_stride;
+    if (o == 2) { const float u = s * 2.0f; return u * u * p.anchors[2 * a]; }
+    if (o == 3) { const float u = s * 2.0f; return u * u * p.anchors[2 * a + 1]; }
+    return s;
 }
 
 
@@ -225,7 +238,7 @@ struct EpiCtx {
 // Epilogue role (mode 0): 2 groups x 4 warps (TMEM lane quarter = warp % 4).  ep_teams: the groups take alternate tiles,
 // otherwise disjoint column segments of every tile.  TMEM -> registers -> bias/act(/extras) -> bf16 -> swizzled staging ->
 // TMA store (two staging buffers per group; the leader lane tracks the bulk groups).
-template <bool EXTRA>
+template <int EXTRA>
 __device__ __forceinline__ void epilogue_store_role(const ConvArgs &p, const EpiCtx &cx) {
     const int e = cx.warp - 2, lane = cx.lane;
     const int grp = e >> 2;
@@ -270,28 +283,25 @@ __device__ __forceinline__ void epilogue_store_role(const ConvArgs &p, const Epi
             ptx::bar_sync(1 + grp, 128);
             const uint32_t rowoff = (uint32_t)row * (uint32_t)(sg.ncol * 2);
             const uint32_t swz = (uint32_t)sg.swz;
+            EpiExtra ex_cur, ex_nxt;
+            epi_fetch<EXTRA>(p, ex_cur, valid, pix, img, tc.nc0 + sg.col0, sg.ncol >= 16 ? 2 : 1);
             for (int c0 = 0; c0 < sg.ncol; c0 += 16) {
                 uint32_t raw[16];
                 const int col = sg.col0 + c0;
-                if (sg.ncol - c0 >= 16) {
-                    ptx::tmem_ld16_nowait(taddr + col, raw);
-                    ptx::tmem_ld_wait();
+                const int halves = sg.ncol - c0 >= 16 ? 2 : 1;
+                if (halves == 2) ptx::tmem_ld16_nowait(taddr + col, raw); else ptx::tmem_ld8_nowait(taddr + col, raw);
+                if (EXTRA && c0 + 16 < sg.ncol) epi_fetch<EXTRA>(p, ex_nxt, valid, pix, img, tc.nc0 + col + 16, sg.ncol - c0 - 16 >= 16 ? 2 : 1);
+                ptx::tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                        const uint4 o = epi_chunk8<EXTRA>(p, raw + 8 * j, sb_tile + (uint32_t)(col + 8 * j) * 4, scale, act, valid, pix,
-                                                          img, tc.nc0 + col + 8 * j);
+                for (int j = 0; j < 2; ++j) {
+                    if (j < halves) {
+                        const uint4 o = epi_chunk8<EXTRA>(raw + 8 * j, sb_tile + (uint32_t)(col + 8 * j) * 4, scale, act, ex_cur, j);
                         uint32_t lin = rowoff + (uint32_t)(c0 * 2 + j * 16);
                         lin ^= ((lin >> 7) & swz) << 4;
                         st_shared_v4(buf + lin, o);
                     }
-                } else {
-                    ptx::tmem_ld8_nowait(taddr + col, raw);
-                    ptx::tmem_ld_wait();
-                    const uint4 o = epi_chunk8<EXTRA>(p, raw, sb_tile + (uint32_t)col * 4, scale, act, valid, pix, img, tc.nc0 + col);
-                    uint32_t lin = rowoff + (uint32_t)(c0 * 2);
-                    lin ^= ((lin >> 7) & swz) << 4;
-                    st_shared_v4(buf + lin, o);
                 }
+                if (EXTRA) ex_cur = ex_nxt;
             }
             if (p.pool) {
                 // fused MaxPool2d(2, 2): the 128-pixel tile is tw x th (both even); 2x2 windows reduced from the staged tile into
@@ -338,32 +348,88 @@ __device__ __forceinline__ void epilogue_store_role(const ConvArgs &p, const Epi
     if (leader) ptx::bulk_wait_read<0>();                     // staging must outlive the last TMA store's read
 }
 
-// Epilogue role (mode 1): Detect decode, direct fp32 stores.  Group g handles accumulator columns [16g, 16g+16).
+// Epilogue role (mode 1): Detect decode.  The 8 epilogue warps split the na*no (= 18) head columns evenly (group g: columns
+// [9g, 9g+9)), decode in registers and write the tile as [anchor][pixel][no] fp32 records into shared memory (decoded and
+// raw); then all 256 threads stream the staged tile out: the 128 pixels of one anchor are ONE contiguous 128*no*4-byte run
+// of `pred` (and of the raw head tensor), written as 16-byte vectors (scalar but still contiguous when the tile straddles
+// two images or the end of the batch).  Two staging buffers: one 256-thread barrier per tile.
+constexpr int kDetHalf = 9;
 __device__ __forceinline__ void epilogue_detect_role(const ConvArgs &p, const EpiCtx &cx) {
     const int e = cx.warp - 2, lane = cx.lane;
     const int grp = e >> 2;
     const int quarter = cx.warp & 3;
     const int row = quarter * 32 + lane;
-    const int w_in = row % p.tw, h_in = (row / p.tw) % p.th, n_in = row / (p.tw * p.th);
+    const int tid = e * 32 + lane;                               // 0..255
     const int n_acc = cx.n_acc;
+    const int no = p.no, nn = p.na * p.no;                       // 6, 18 for the Rep-YOLO head
+    const int rec = 128 * no;                                    // floats per anchor per tile
+    const int tile_f = p.na * rec;                               // floats per staged tile (one of decoded / raw)
+    const int col0 = grp * kDetHalf;
+    const int ldcol = grp ? kDetHalf - 1 : 0;                    // 16-column TMEM load window [ldcol, ldcol + 16) covers the group's columns
+    float *stage = reinterpret_cast<float *>(cx.sStage);
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(p.pred) | reinterpret_cast<uintptr_t>(p.raw)) & 15) == 0 && (rec % 4) == 0 &&
+                        ((p.img_hw * no) % 4) == 0 && (((size_t)p.rows_total * no) % 4) == 0 && (((size_t)p.row_off * no) % 4) == 0;
     int it = 0;
     for (int t = blockIdx.x; t < cx.total_tiles; t += gridDim.x, ++it) {
         const int acc = n_acc == 4 ? (it & 3) : (it & 1);
         const uint32_t aph = (uint32_t)(n_acc == 4 ? (it >> 2) : (it >> 1)) & 1u;
-        const TileCoord tc = tile_coord(p, t);
-        const int w = tc.w0 + w_in, h = tc.h0 + h_in, n = tc.n0 + n_in;
-        const bool valid = (n_in < p.tn) && (w < p.Wo) && (h < p.Ho) && (n < p.Bo);
-        const size_t pix = ((size_t)n * p.Ho + h) * p.Wo + w;
+        const TileCoord tc = tile_coord(p, t);                   // 1x1 conv: flat pixel tiles, tc.w0 = first pixel
+        float *sp = stage + (size_t)(it & 1) * 2 * tile_f, *sr = sp + tile_f;
         ptx::mbar_wait(cx.tfull + acc, aph);
         ptx::tc_fence_after();
         const uint32_t taddr = cx.tmem_base + acc * p.BN + ((uint32_t)(quarter * 32) << 16);
         uint32_t raw[16];
-        ptx::tmem_ld16_nowait(taddr + grp * 16, raw);
+        ptx::tmem_ld16_nowait(taddr + ldcol, raw);
         ptx::tmem_ld_wait();
-        if (valid && grp * 16 < p.cout) detect_epilogue(p, raw, grp * 16, pix);
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(cx.tempty + acc);
+        if (lane == 0) ptx::mbar_arrive(cx.tempty + acc);        // accumulator is in registers: the MMA warp may reuse the stage
+        {
+            const uint32_t pix = (uint32_t)tc.w0 + (uint32_t)row;
+            const int b = (int)(((uint64_t)pix * p.div_hw) >> 40);
+            const int rem = (int)(pix - (uint32_t)b * (uint32_t)p.img_hw);
+            const int gy = rem / p.img_w, gx = rem - gy * p.img_w;
+#pragma unroll
+            for (int i = 0; i < kDetHalf; ++i) {
+                const int j = col0 + i;
+                if (j < nn) {
+                    const int a = j / no, o = j - a * no;
+                    const float tv = __uint_as_float(raw[j - ldcol]) + ld_shared_f(cx.sbias_u + (uint32_t)j * 4);
+                    sr[a * rec + row * no + o] = tv;
+                    sp[a * rec + row * no + o] = detect_decode(p, tv, a, o, gx, gy);
+                }
+            }
+        }
+        ptx::bar_sync(1, 256);
+        const uint32_t pix0 = (uint32_t)tc.w0;
+        const int b0 = (int)(((uint64_t)pix0 * p.div_hw) >> 40);
+        const int rem0 = (int)(pix0 - (uint32_t)b0 * (uint32_t)p.img_hw);
+        const bool whole = vec_ok && rem0 + 128 <= p.img_hw && (int)pix0 + 128 <= p.Wo;     // one image, no batch tail
+        const int n_out = p.raw != nullptr ? 2 : 1;
+        if (whole) {
+            const int vpa = rec / 4;                             // 16-byte vectors per anchor
+            for (int v = tid; v < n_out * p.na * vpa; v += 256) {
+                const int which = v / (p.na * vpa), vv = v - which * p.na * vpa;
+                const int a = vv / vpa, q = vv - a * vpa;
+                const float4 val = *reinterpret_cast<const float4 *>((which ? sr : sp) + a * rec + q * 4);
+                float *dst = which ? p.raw + (((size_t)b0 * p.na + a) * p.img_hw + rem0) * no
+                                   : p.pred + ((size_t)b0 * p.rows_total + p.row_off + (size_t)a * p.img_hw + rem0) * no;
+                *reinterpret_cast<float4 *>(dst + q * 4) = val;
+            }
+        } else {
+            for (int v = tid; v < n_out * tile_f; v += 256) {
+                const int which = v / tile_f, vv = v - which * tile_f;
+                const int a = vv / rec, q = vv - a * rec;
+                const int r = q / no, o = q - r * no;
+                const uint32_t pix = pix0 + (uint32_t)r;
+                if ((int)pix >= p.Wo) continue;
+                const int b = (int)(((uint64_t)pix * p.div_hw) >> 40);
+                const int rem = (int)(pix - (uint32_t)b * (uint32_t)p.img_hw);
+                const float val = (which ? sr : sp)[vv];
+                if (which) p.raw[(((size_t)b * p.na + a) * p.img_hw + rem) * no + o] = val;
+                else p.pred[((size_t)b * p.rows_total + p.row_off + (size_t)a * p.img_hw + rem) * no + o] = val;
+            }
+        }
     }
 }
 
@@ -497,8 +563,9 @@ __global__ void __launch_bounds__(kConvMaxThreads, 1) conv_umma_kernel(const __g
         cx.warp = warp; cx.lane = lane;
         pdl_wait();                 // residual / per-image vector reads and all output writes come after the prerequisites
         if (p.mode != 0) epilogue_detect_role(p, cx);
-        else if (p.res != nullptr || p.bvec != nullptr) epilogue_store_role<true>(p, cx);
-        else epilogue_store_role<false>(p, cx);
+        else if (p.res != nullptr) epilogue_store_role<1>(p, cx);
+        else if (p.bvec != nullptr) epilogue_store_role<2>(p, cx);
+        else epilogue_store_role<0>(p, cx);
     }
 
     ptx::tc_fence_before();
@@ -523,7 +590,8 @@ int conv_plan_smem(ConvArgs &a, int max_seg_cols) {
     a.a_box_bytes = box_rows * rb;
     a.a_stage_bytes = a.a_mode == A_HALO ? ((a.a_box_bytes + 1023) & ~1023) : 128 * rb;
     a.b_stage_bytes = a.BN * rb;
-    a.stage_buf_bytes = a.mode == 0 ? (((a.pool ? 160 : 128) * max_seg_cols * 2 + 1023) & ~1023) : 0;   // + pooled tile behind it
+    a.stage_buf_bytes = a.mode == 0 ? (((a.pool ? 160 : 128) * max_seg_cols * 2 + 1023) & ~1023)   // + pooled tile behind it
+                                    : ((a.na * 128 * a.no * 4 + 1023) & ~1023);                    // Detect: 2 buffers x (decoded, raw) tiles
     const long fixed = 4L * a.stage_buf_bytes + ((a.cout_pad * 4 + 127) & ~127) + kBarrierBytes + 1024;
     const long avail = kSmemLimit - fixed;
     const long b_total = (long)a.kblocks * a.b_stage_bytes;

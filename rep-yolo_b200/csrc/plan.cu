@@ -476,6 +476,7 @@ int bind_conv(ry_plan *p, Op &op, std::vector<CUtensorMap> &maps) {
         }
         maps.push_back(m);
     }
+    if (cp.n_src <= 1 && d.in1.tensor >= 0 && d.in2.tensor >= 0) RY_FAIL("conv: residual and per-image vector in one epilogue is not built");
     if (cp.n_src <= 1 && d.in1.tensor >= 0) {
         a.res = bf(p, d.in1.tensor);
         a.res_cs = p->tensors[d.in1.tensor].d.channels;
