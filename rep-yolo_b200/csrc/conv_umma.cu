@@ -54,8 +54,10 @@ struct EpiExtra {
 };
 
 // EXTRA: bit 0 = residual, bit 1 = per-image vector (compile time, so the unused operand costs no registers)
+// sbv_row: shared-memory address of the staged per-image vector of this row's image (0: not staged, read global memory)
 template <int EXTRA>
-__device__ __forceinline__ void epi_fetch(const ConvArgs &p, EpiExtra &x, bool valid, size_t pix, int img, int ch, int halves) {
+__device__ __forceinline__ void epi_fetch(const ConvArgs &p, EpiExtra &x, bool valid, size_t pix, int img, int ch, int halves,
+                                          uint32_t sbv_row) {
     if (!EXTRA) return;
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
@@ -64,9 +66,14 @@ __device__ __forceinline__ void epi_fetch(const ConvArgs &p, EpiExtra &x, bool v
         if (valid && j < halves) {
             if (EXTRA & 1) x.r[j] = __ldg(reinterpret_cast<const uint4 *>(p.res + pix * p.res_cs + p.res_off + ch + 8 * j));
             if (EXTRA & 2) {
-                const float4 *bv = reinterpret_cast<const float4 *>(p.bvec + (size_t)img * p.bvec_cs + p.bvec_off + ch + 8 * j);
-                x.v[2 * j] = __ldg(bv);
-                x.v[2 * j + 1] = __ldg(bv + 1);
+                if (sbv_row) {
+                    x.v[2 * j] = ld_shared_f4(sbv_row + (uint32_t)(ch + 8 * j) * 4);
+                    x.v[2 * j + 1] = ld_shared_f4(sbv_row + (uint32_t)(ch + 8 * j) * 4 + 16);
+                } else {
+                    const float4 *bv = reinterpret_cast<const float4 *>(p.bvec + (size_t)img * p.bvec_cs + p.bvec_off + ch + 8 * j);
+                    x.v[2 * j] = __ldg(bv);
+                    x.v[2 * j + 1] = __ldg(bv + 1);
+                }
             }
         }
     }
@@ -106,7 +113,7 @@ __device__ __forceinline__ uint4 epi_chunk8(const uint32_t *raw, uint32_t sb_add
 
 // IDetect.fuseforward decode (reference models/yolo.py:139-156): same op order, fp32.
 __device__ __forceinline__ float detect_decode(const ConvArgs &p, float t, int a, int o, int gx, int gy) {
-    const float s = 1.0f / (1.0f + expf(-t));
+    const float s = __fdividef(1.0f, 1.0f + __expf(-t));        // |error| ~1e-7, far inside the stated decode tolerance
     if (o == 0) return (s * 2.0f - 0.5f + (float)gx) * p.det_stride;
     if (o == 1) return (s * 2.0f - 0.5f + (float)gy) * p.det_stride;
     if (o == 2) { const float u = s * 2.0f; return u * u * p.anchors[2 * a]; }
@@ -118,7 +125,7 @@ __device__ __forceinline__ float detect_decode(const ConvArgs &p, float t, int a
 struct MmaCtx {
     uint64_t *fullA, *emptyA, *fullB, *emptyB, *tfull, *tempty, *bres;
     uint32_t sA_u, sB_u, tmem_base;
-    int total_tiles, n_acc;
+    int t_begin, t_end, t_step, n_acc;
 };
 
 // One tap / K block: KS K=16 steps into the same accumulator; the first step takes the run-time accumulate flag.
@@ -154,7 +161,7 @@ __device__ __forceinline__ void mma_role(const ConvArgs &p, const MmaCtx &cx) {
     }
     int sa = 0, sb = 0, acc = 0;
     uint32_t pha = 0, phb = 0, aph = 0;
-    for (int t = blockIdx.x; t < cx.total_tiles; t += gridDim.x) {
+    for (int t = cx.t_begin; t < cx.t_end; t += cx.t_step) {
         ptx::mbar_wait(cx.tempty + acc, aph ^ 1);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_u + acc * p.BN;
@@ -232,7 +239,8 @@ struct EpiCtx {
     uint64_t *tfull, *tempty;
     uint32_t tmem_base, stage_u, sbias_u;
     uint8_t *sStage;
-    int total_tiles, n_acc, warp, lane;
+    float *sbv;
+    int t_begin, t_end, t_step, n_acc, warp, lane;
 };
 
 // Epilogue role (mode 0): 2 groups x 4 warps (TMEM lane quarter = warp % 4).  ep_teams: the groups take alternate tiles,
@@ -255,7 +263,10 @@ __device__ __forceinline__ void epilogue_store_role(const ConvArgs &p, const Epi
     const int n_acc = cx.n_acc;
     const int gmask = p.n_groups - 1;
     int bufsel = 0, it = 0;
-    for (int t = blockIdx.x; t < cx.total_tiles; t += gridDim.x, ++it) {
+    int bv_img = -1;                                          // image whose vector (and its successor's) is staged
+    float *sbv = cx.sbv + (size_t)grp * 2 * p.cout_pad;
+    const uint32_t sbv_u = ptx::smem_u32(sbv);
+    for (int t = cx.t_begin; t < cx.t_end; t += cx.t_step, ++it) {
         if (p.ep_teams && (it & gmask) != grp) continue;      // tile teams
         const int acc = n_acc == 4 ? (it & 3) : (it & 1);
         const uint32_t aph = (uint32_t)(n_acc == 4 ? (it >> 2) : (it >> 1)) & 1u;
@@ -269,6 +280,24 @@ __device__ __forceinline__ void epilogue_store_role(const ConvArgs &p, const Epi
             const uint32_t pix32 = ((uint32_t)n * (uint32_t)p.Ho + (uint32_t)h) * (uint32_t)p.Wo + (uint32_t)w;   // < 2^31 pixels per batch
             pix = pix32;
             img = (int)(((uint64_t)pix32 * p.div_hw) >> 40);
+        }
+        uint32_t sbv_row = 0;
+        if (EXTRA & 2) {
+            // per-image vectors of the tile's first image and the next one staged in shared memory (the operand is the same
+            // for all rows of an image; with ~200 KB of shared memory in use there is hardly any L1 left to catch the re-reads)
+            const uint32_t pix0 = ((uint32_t)tc.n0 * (uint32_t)p.Ho + (uint32_t)tc.h0) * (uint32_t)p.Wo + (uint32_t)tc.w0;
+            const int img0 = (int)(((uint64_t)pix0 * p.div_hw) >> 40);
+            if (img0 != bv_img) {
+                ptx::bar_sync(1 + grp, 128);                      // nobody still reads the previous pair
+                for (int i = (e & 3) * 32 + lane; i < 2 * p.cout_pad; i += 128) {
+                    const int second = i >= p.cout_pad ? 1 : 0, c = i - second * p.cout_pad;
+                    sbv[i] = (c < p.cout && img0 + second < p.n_img) ? __ldg(p.bvec + (size_t)(img0 + second) * p.bvec_cs + p.bvec_off + c) : 0.0f;
+                }
+                ptx::bar_sync(1 + grp, 128);
+                bv_img = img0;
+            }
+            const int dimg = img - img0;
+            if (dimg == 0 || dimg == 1) sbv_row = sbv_u + (uint32_t)(dimg * p.cout_pad) * 4;
         }
         ptx::mbar_wait(cx.tfull + acc, aph);
         ptx::tc_fence_after();
@@ -284,13 +313,13 @@ __device__ __forceinline__ void epilogue_store_role(const ConvArgs &p, const Epi
             const uint32_t rowoff = (uint32_t)row * (uint32_t)(sg.ncol * 2);
             const uint32_t swz = (uint32_t)sg.swz;
             EpiExtra ex_cur, ex_nxt;
-            epi_fetch<EXTRA>(p, ex_cur, valid, pix, img, tc.nc0 + sg.col0, sg.ncol >= 16 ? 2 : 1);
+            epi_fetch<EXTRA>(p, ex_cur, valid, pix, img, tc.nc0 + sg.col0, sg.ncol >= 16 ? 2 : 1, sbv_row);
             for (int c0 = 0; c0 < sg.ncol; c0 += 16) {
                 uint32_t raw[16];
                 const int col = sg.col0 + c0;
                 const int halves = sg.ncol - c0 >= 16 ? 2 : 1;
                 if (halves == 2) ptx::tmem_ld16_nowait(taddr + col, raw); else ptx::tmem_ld8_nowait(taddr + col, raw);
-                if (EXTRA && c0 + 16 < sg.ncol) epi_fetch<EXTRA>(p, ex_nxt, valid, pix, img, tc.nc0 + col + 16, sg.ncol - c0 - 16 >= 16 ? 2 : 1);
+                if (EXTRA && c0 + 16 < sg.ncol) epi_fetch<EXTRA>(p, ex_nxt, valid, pix, img, tc.nc0 + col + 16, sg.ncol - c0 - 16 >= 16 ? 2 : 1, sbv_row);
                 ptx::tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
@@ -353,7 +382,9 @@ __device__ __forceinline__ void epilogue_store_role(const ConvArgs &p, const Epi
 // raw); then all 256 threads stream the staged tile out: the 128 pixels of one anchor are ONE contiguous 128*no*4-byte run
 // of `pred` (and of the raw head tensor), written as 16-byte vectors (scalar but still contiguous when the tile straddles
 // two images or the end of the batch).  Two staging buffers: one 256-thread barrier per tile.
+// NO6 = true: the Rep-YOLO head (na = 3, no = 6) with every index computation on compile-time constants.
 constexpr int kDetHalf = 9;
+template <bool NO6>
 __device__ __forceinline__ void epilogue_detect_role(const ConvArgs &p, const EpiCtx &cx) {
     const int e = cx.warp - 2, lane = cx.lane;
     const int grp = e >> 2;
@@ -361,16 +392,16 @@ __device__ __forceinline__ void epilogue_detect_role(const ConvArgs &p, const Ep
     const int row = quarter * 32 + lane;
     const int tid = e * 32 + lane;                               // 0..255
     const int n_acc = cx.n_acc;
-    const int no = p.no, nn = p.na * p.no;                       // 6, 18 for the Rep-YOLO head
+    const int no = NO6 ? 6 : p.no, na = NO6 ? 3 : p.na, nn = na * no;
     const int rec = 128 * no;                                    // floats per anchor per tile
-    const int tile_f = p.na * rec;                               // floats per staged tile (one of decoded / raw)
+    const int tile_f = na * rec;                                 // floats per staged tile (one of decoded / raw)
     const int col0 = grp * kDetHalf;
     const int ldcol = grp ? kDetHalf - 1 : 0;                    // 16-column TMEM load window [ldcol, ldcol + 16) covers the group's columns
     float *stage = reinterpret_cast<float *>(cx.sStage);
     const bool vec_ok = ((reinterpret_cast<uintptr_t>(p.pred) | reinterpret_cast<uintptr_t>(p.raw)) & 15) == 0 && (rec % 4) == 0 &&
                         ((p.img_hw * no) % 4) == 0 && (((size_t)p.rows_total * no) % 4) == 0 && (((size_t)p.row_off * no) % 4) == 0;
     int it = 0;
-    for (int t = blockIdx.x; t < cx.total_tiles; t += gridDim.x, ++it) {
+    for (int t = cx.t_begin; t < cx.t_end; t += cx.t_step, ++it) {
         const int acc = n_acc == 4 ? (it & 3) : (it & 1);
         const uint32_t aph = (uint32_t)(n_acc == 4 ? (it >> 2) : (it >> 1)) & 1u;
         const TileCoord tc = tile_coord(p, t);                   // 1x1 conv: flat pixel tiles, tc.w0 = first pixel
@@ -388,13 +419,13 @@ __device__ __forceinline__ void epilogue_detect_role(const ConvArgs &p, const Ep
             const uint32_t pix = (uint32_t)tc.w0 + (uint32_t)row;
             const int b = (int)(((uint64_t)pix * p.div_hw) >> 40);
             const int rem = (int)(pix - (uint32_t)b * (uint32_t)p.img_hw);
-            const int gy = rem / p.img_w, gx = rem - gy * p.img_w;
+            const int gy = (int)fast_div((uint32_t)rem, p.div_imgw), gx = rem - gy * p.img_w;
 #pragma unroll
             for (int i = 0; i < kDetHalf; ++i) {
                 const int j = col0 + i;
                 if (j < nn) {
                     const int a = j / no, o = j - a * no;
-                    const float tv = __uint_as_float(raw[j - ldcol]) + ld_shared_f(cx.sbias_u + (uint32_t)j * 4);
+                    const float tv = __uint_as_float(grp ? raw[i + 1] : raw[i]) + ld_shared_f(cx.sbias_u + (uint32_t)j * 4);   // raw[j - ldcol]
                     sr[a * rec + row * no + o] = tv;
                     sp[a * rec + row * no + o] = detect_decode(p, tv, a, o, gx, gy);
                 }
@@ -408,17 +439,17 @@ __device__ __forceinline__ void epilogue_detect_role(const ConvArgs &p, const Ep
         const int n_out = p.raw != nullptr ? 2 : 1;
         if (whole) {
             const int vpa = rec / 4;                             // 16-byte vectors per anchor
-            for (int v = tid; v < n_out * p.na * vpa; v += 256) {
-                const int which = v / (p.na * vpa), vv = v - which * p.na * vpa;
+            for (int v = tid; v < n_out * na * vpa; v += 256) {
+                const int which = v >= na * vpa ? 1 : 0, vv = v - which * na * vpa;
                 const int a = vv / vpa, q = vv - a * vpa;
                 const float4 val = *reinterpret_cast<const float4 *>((which ? sr : sp) + a * rec + q * 4);
-                float *dst = which ? p.raw + (((size_t)b0 * p.na + a) * p.img_hw + rem0) * no
+                float *dst = which ? p.raw + (((size_t)b0 * na + a) * p.img_hw + rem0) * no
                                    : p.pred + ((size_t)b0 * p.rows_total + p.row_off + (size_t)a * p.img_hw + rem0) * no;
                 *reinterpret_cast<float4 *>(dst + q * 4) = val;
             }
         } else {
             for (int v = tid; v < n_out * tile_f; v += 256) {
-                const int which = v / tile_f, vv = v - which * tile_f;
+                const int which = v >= tile_f ? 1 : 0, vv = v - which * tile_f;
                 const int a = vv / rec, q = vv - a * rec;
                 const int r = q / no, o = q - r * no;
                 const uint32_t pix = pix0 + (uint32_t)r;
@@ -426,7 +457,7 @@ __device__ __forceinline__ void epilogue_detect_role(const ConvArgs &p, const Ep
                 const int b = (int)(((uint64_t)pix * p.div_hw) >> 40);
                 const int rem = (int)(pix - (uint32_t)b * (uint32_t)p.img_hw);
                 const float val = (which ? sr : sp)[vv];
-                if (which) p.raw[(((size_t)b * p.na + a) * p.img_hw + rem) * no + o] = val;
+                if (which) p.raw[(((size_t)b * na + a) * p.img_hw + rem) * no + o] = val;
                 else p.pred[((size_t)b * p.rows_total + p.row_off + (size_t)a * p.img_hw + rem) * no + o] = val;
             }
         }
@@ -441,7 +472,8 @@ __global__ void __launch_bounds__(kConvMaxThreads, 1) conv_umma_kernel(const __g
     uint8_t *sB = sA + (size_t)p.a_stages * p.a_stage_bytes;
     uint8_t *sStage = sB + (size_t)nb_slots * p.b_stage_bytes;
     float *sbias = reinterpret_cast<float *>(sStage + (size_t)(p.n_groups == 4 ? 4 : 4) * p.stage_buf_bytes);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(sbias) + ((p.cout_pad * 4 + 127) & ~127));
+    float *sbv = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(sbias) + ((p.cout_pad * 4 + 127) & ~127));
+    uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(sbv) + p.bv_bytes);
     uint64_t *fullA = bars, *emptyA = fullA + 8, *fullB = emptyA + 8, *emptyB = fullB + 8;
     uint64_t *tfull = emptyB + 8, *tempty = tfull + 4, *bres = tempty + 4;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bres + 1);
@@ -449,6 +481,15 @@ __global__ void __launch_bounds__(kConvMaxThreads, 1) conv_umma_kernel(const __g
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rb = p.kb * 2;                                   // bytes per operand row == swizzle span
     const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_ntiles;
+    // tile -> CTA: round robin (neighbouring CTAs work on neighbouring tiles: halo / weight reuse in L2), or one contiguous
+    // range per CTA (per-image epilogue operands staged in shared memory change once per image instead of once per tile)
+    int t_begin = blockIdx.x, t_end = total_tiles, t_step = gridDim.x;
+    if (p.tile_contig) {
+        const int per = (total_tiles + gridDim.x - 1) / gridDim.x;
+        t_begin = blockIdx.x * per;
+        t_end = min(total_tiles, t_begin + per);
+        t_step = 1;
+    }
     const int n_acc = p.n_acc;                                  // TMEM accumulator stages (MMA runs ahead of the epilogue)
     uint32_t tmem_cols = 32;
     while (tmem_cols < (uint32_t)(n_acc * p.BN)) tmem_cols <<= 1;
@@ -496,7 +537,7 @@ __global__ void __launch_bounds__(kConvMaxThreads, 1) conv_umma_kernel(const __g
         uint32_t pha = 0, phb = 0;
         const bool stream_b = !p.b_resident;
         pdl_wait();                 // activations are written by earlier kernels (weights above are constants)
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        for (int t = t_begin; t < t_end; t += t_step) {
             const TileCoord tc = tile_coord(p, t);
             if (p.a_mode == A_HALO) {
                 for (int c = 0; c < p.cblk; ++c) {
@@ -548,7 +589,7 @@ __global__ void __launch_bounds__(kConvMaxThreads, 1) conv_umma_kernel(const __g
         // ===================== MMA issuer =====================
         MmaCtx cx;
         cx.fullA = fullA; cx.emptyA = emptyA; cx.fullB = fullB; cx.emptyB = emptyB; cx.tfull = tfull; cx.tempty = tempty; cx.bres = bres;
-        cx.sA_u = ptx::smem_u32(sA); cx.sB_u = ptx::smem_u32(sB); cx.tmem_base = tmem_base; cx.total_tiles = total_tiles; cx.n_acc = n_acc;
+        cx.sA_u = ptx::smem_u32(sA); cx.sB_u = ptx::smem_u32(sB); cx.tmem_base = tmem_base; cx.t_begin = t_begin; cx.t_end = t_end; cx.t_step = t_step; cx.n_acc = n_acc;
         if (p.a_mode == A_HALO) {
             if (p.b_resident) mma_role_ks<true, false>(p, cx); else mma_role_ks<true, true>(p, cx);
         } else {
@@ -559,10 +600,10 @@ __global__ void __launch_bounds__(kConvMaxThreads, 1) conv_umma_kernel(const __g
         // ===================== epilogue =====================
         EpiCtx cx;
         cx.tfull = tfull; cx.tempty = tempty; cx.tmem_base = tmem_base; cx.stage_u = ptx::smem_u32(sStage);
-        cx.sbias_u = ptx::smem_u32(sbias); cx.sStage = sStage; cx.total_tiles = total_tiles; cx.n_acc = n_acc;
+        cx.sbias_u = ptx::smem_u32(sbias); cx.sStage = sStage; cx.sbv = sbv; cx.t_begin = t_begin; cx.t_end = t_end; cx.t_step = t_step; cx.n_acc = n_acc;
         cx.warp = warp; cx.lane = lane;
         pdl_wait();                 // residual / per-image vector reads and all output writes come after the prerequisites
-        if (p.mode != 0) epilogue_detect_role(p, cx);
+        if (p.mode != 0) { if (p.no == 6 && p.na == 3) epilogue_detect_role<true>(p, cx); else epilogue_detect_role<false>(p, cx); }
         else if (p.res != nullptr) epilogue_store_role<1>(p, cx);
         else if (p.bvec != nullptr) epilogue_store_role<2>(p, cx);
         else epilogue_store_role<0>(p, cx);
@@ -581,7 +622,7 @@ __global__ void __launch_bounds__(kConvMaxThreads, 1) conv_umma_kernel(const __g
 size_t conv_smem_bytes(const ConvArgs &a) {
     const int nb = a.b_resident ? a.kblocks : a.b_stages;
     return (size_t)a.a_stages * a.a_stage_bytes + (size_t)nb * a.b_stage_bytes + 4 * (size_t)a.stage_buf_bytes +   // 2x2 or 4x1 buffers
-           ((a.cout_pad * 4 + 127) & ~127) + kBarrierBytes + 1024;
+           ((a.cout_pad * 4 + 127) & ~127) + a.bv_bytes + kBarrierBytes + 1024;
 }
 
 int conv_plan_smem(ConvArgs &a, int max_seg_cols) {
@@ -592,7 +633,7 @@ int conv_plan_smem(ConvArgs &a, int max_seg_cols) {
     a.b_stage_bytes = a.BN * rb;
     a.stage_buf_bytes = a.mode == 0 ? (((a.pool ? 160 : 128) * max_seg_cols * 2 + 1023) & ~1023)   // + pooled tile behind it
                                     : ((a.na * 128 * a.no * 4 + 1023) & ~1023);                    // Detect: 2 buffers x (decoded, raw) tiles
-    const long fixed = 4L * a.stage_buf_bytes + ((a.cout_pad * 4 + 127) & ~127) + kBarrierBytes + 1024;
+    const long fixed = 4L * a.stage_buf_bytes + ((a.cout_pad * 4 + 127) & ~127) + a.bv_bytes + kBarrierBytes + 1024;
     const long avail = kSmemLimit - fixed;
     const long b_total = (long)a.kblocks * a.b_stage_bytes;
     const int a_per_tile = a.a_mode == A_HALO ? a.cblk : a.kblocks;

@@ -58,6 +58,7 @@ struct ConvArgs {
     int tw, th, tn;            // output tile extent in w, h, image
     int tiles_w, tiles_h, tiles_n;
     uint64_t div_hw;           // ceil(2^40 / img_hw): image index of a pixel = (pix * div_hw) >> 40
+    uint32_t div_imgw;         // ceil(2^32 / img_w) (0 when img_w == 1): row of a pixel inside its image (Detect grid)
     uint32_t div_nt, div_tw, div_th;   // ceil(2^32 / d) for d = n_ntiles, tiles_w, tiles_h (0 when d == 1): exact q = umulhi(n, m)
     int n_ntiles, BN;          // output-channel tiling
     int Wo, Ho, Bo;            // logical output extent the tile grid covers (1x1: Wo = B*H*W, Ho = Bo = 1)
@@ -81,6 +82,9 @@ struct ConvArgs {
     int res_cs, res_off;
     const float *bvec;         // optional per-image vector [B][bvec_cs], added after the activation
     int bvec_cs, bvec_off;
+    int bv_bytes;              // shared-memory copy of the per-image vectors of a tile's (up to two) images: 4 groups x 2 x cout_pad fp32
+    int n_img;                 // images in the batch (bound of the staged second image)
+    int tile_contig;           // 1: every CTA takes one contiguous range of tiles instead of every gridDim-th tile
     float *pred, *raw;         // Detect outputs
     int no, na, row_off, rows_total;
     float det_stride;

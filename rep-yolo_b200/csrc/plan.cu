@@ -389,6 +389,7 @@ int bind_conv(ry_plan *p, Op &op, std::vector<CUtensorMap> &maps) {
     if (acc_env && atoi(acc_env) == 2) a.n_acc = 2;
     a.tiles_w = cdiv(a.Wo, a.tw); a.tiles_h = cdiv(a.Ho, a.th); a.tiles_n = cdiv(a.Bo, a.tn);
     a.div_hw = (uint64_t)(((1ull << 40) + (uint64_t)a.img_hw - 1) / (uint64_t)a.img_hw);
+    a.div_imgw = a.img_w <= 1 ? 0u : (uint32_t)(((1ull << 32) + (uint64_t)a.img_w - 1) / (uint64_t)a.img_w);
     {
         auto magic = [](int d) -> uint32_t { return d <= 1 ? 0u : (uint32_t)(((1ull << 32) + (uint64_t)d - 1) / (uint64_t)d); };
         a.div_nt = magic(a.n_ntiles); a.div_tw = magic(a.tiles_w); a.div_th = magic(a.tiles_h);
@@ -436,6 +437,9 @@ int bind_conv(ry_plan *p, Op &op, std::vector<CUtensorMap> &maps) {
         pieces[0] = {0, cp.BN, d.out0.c_off, 0};                    // per N tile; channels past the view are clipped by the map
         c_end = (cuuint64_t)(d.out0.c_off + d.out0.c_len);
     }
+    a.bv_bytes = (cp.n_src <= 1 && d.in2.tensor >= 0) ? 4 * 2 * cp.cout_pad * 4 : 0;
+    a.n_img = B;
+    a.tile_contig = a.bv_bytes ? 1 : 0;
     int widths[8], n_widths = 0;
     int max_cols = 64;
     build_segments(a, pieces, n_pieces, max_cols, widths, &n_widths);
