@@ -136,6 +136,11 @@ int pack_conv(const ry_op_desc &d, const unsigned char *host, size_t host_bytes,
     const int c16 = (cout + 15) / 16 * 16;
     cp.BN = c16 <= 256 ? c16 : 256;
     if (c16 > 256 && c16 % 256 != 0) cp.BN = 128;
+    {   // HBM-bound 256-wide 1x1 layers: two 128-wide N tiles so that four epilogue teams (4 x 128 TMEM columns) work in parallel
+        static const double ai_max = getenv("RY_CONV_SPLIT256_AI") ? atof(getenv("RY_CONV_SPLIT256_AI")) : 160.0;
+        const double ai = (double)cin * cout * k * k / (double)(cin + cout);      // FLOP per byte of activation traffic
+        if (c16 == 256 && k == 1 && d.kind == RY_OP_CONV && d.out1.tensor < 0 && ai < ai_max) cp.BN = 128;
+    }
     cp.n_ntiles = (c16 + cp.BN - 1) / cp.BN;
     cp.cout_pad = cp.n_ntiles * cp.BN;
     const float *w = reinterpret_cast<const float *>(host + d.w_off);
@@ -248,8 +253,10 @@ void build_segments(ConvArgs &a, const OutPiece *pieces, int n_pieces, int max_c
     std::vector<S> segs;
     // small N: one segment per output piece (dense rows unless the width is a power of two), the two epilogue groups work
     // as teams on alternate tiles; otherwise power-of-two segments spread over two column groups
-    a.ep_teams = (total <= 64 && n_pieces <= kConvMaxSegs) ? 1 : 0;
-    if (a.ep_teams) {
+    static const int teams_max = getenv("RY_CONV_TEAMS_MAX") ? atoi(getenv("RY_CONV_TEAMS_MAX")) : 128;
+    a.ep_teams = (total <= std::max(64, teams_max) && 4 * a.BN <= 512 && n_pieces <= kConvMaxSegs) ? 1 : 0;
+    if (total <= 64 && n_pieces > kConvMaxSegs) a.ep_teams = 0;
+    if (a.ep_teams && total <= 64) {
         for (int i = 0; i < n_pieces; ++i) segs.push_back({pieces[i].col0, pieces[i].len, pieces[i].chan, pieces[i].slot});
     } else {
         int wmax = 8;
