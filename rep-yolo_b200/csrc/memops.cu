@@ -175,15 +175,31 @@ __global__ void __launch_bounds__(256) stem_kernel(const void *__restrict__ img_
 #pragma unroll
                 for (int r = 0; r < 2; ++r) {
                     const int pix = trow * kStemTW + px0 + g + 8 * r;
-                    st[(pix * COUT + nt * 8 + 2 * t4) >> 1] = pack_bf16x2(silu_f(acc[nt][2 * r]), silu_f(acc[nt][2 * r + 1]));
+                    // SiLU(x) = h + h * tanh(h), h = x / 2 (one MUFU; error below the bf16 rounding of the result)
+                    const float h0 = 0.5f * acc[nt][2 * r], h1 = 0.5f * acc[nt][2 * r + 1];
+                    st[(pix * COUT + nt * 8 + 2 * t4) >> 1] = pack_bf16x2(fmaf(h0, tanh_approx_f(h0), h0), fmaf(h1, tanh_approx_f(h1), h1));
                 }
             __syncthreads();
             constexpr int CPP = COUT / 8;                   // 16-byte chunks per pixel
-            for (int i = threadIdx.x; i < 2 * kStemTW * CPP; i += 256) {
-                const int pix = i / CPP, ch = i % CPP;
-                const int ho = ho0 + 2 * rp + pix / kStemTW, wo = wo0 + pix % kStemTW;
-                if (ho < Ho && wo < Wo)
-                    stg16(out + (((size_t)b * Ho + ho) * Wo + wo) * out_cs + out_off + ch * 8, reinterpret_cast<const uint4 *>(stage)[i]);
+            constexpr int RowV = kStemTW * CPP;             // 16-byte chunks per staged row
+            if (out_cs == COUT && wo0 + kStemTW <= Wo) {
+                // dense output, full-width tile: a staged row is one contiguous run of the output map
+#pragma unroll
+                for (int rr = 0; rr < 2; ++rr) {
+                    const int ho = ho0 + 2 * rp + rr;
+                    if (ho < Ho) {
+                        uint4 *dst = reinterpret_cast<uint4 *>(out + (((size_t)b * Ho + ho) * Wo + wo0) * COUT + out_off);
+                        const uint4 *srcv = reinterpret_cast<const uint4 *>(stage) + rr * RowV;
+                        for (int i = threadIdx.x; i < RowV; i += 256) dst[i] = srcv[i];
+                    }
+                }
+            } else {
+                for (int i = threadIdx.x; i < 2 * RowV; i += 256) {
+                    const int pix = i / CPP, ch = i % CPP;
+                    const int ho = ho0 + 2 * rp + pix / kStemTW, wo = wo0 + pix % kStemTW;
+                    if (ho < Ho && wo < Wo)
+                        stg16(out + (((size_t)b * Ho + ho) * Wo + wo) * out_cs + out_off + ch * 8, reinterpret_cast<const uint4 *>(stage)[i]);
+                }
             }
         }
         __syncthreads();                                    // this buffer / staging are free for the next iteration

@@ -253,84 +253,109 @@ __global__ void __launch_bounds__(kChunk) nms_scan_kernel(const float *__restric
                                                           int agnostic, int max_det, int max_nms, float *__restrict__ out,
                                                           int *__restrict__ out_counts) {
     extern __shared__ unsigned char smraw[];
-    // chunk boxes (SoA) | mask | kept boxes (SoA) | control
+    // survivor boxes of the chunk (SoA) | mask | kept boxes (SoA) | control
     float *cx1 = reinterpret_cast<float *>(smraw), *cy1 = cx1 + kChunk, *cx2 = cy1 + kChunk, *cy2 = cx2 + kChunk, *car = cy2 + kChunk;
-    unsigned long long *mask = reinterpret_cast<unsigned long long *>(car + kChunk);       // [kChunk][kChunkWords]
-    unsigned long long *dead = mask + (size_t)kChunk * kChunkWords;                          // [kChunkWords]
-    float *kx1 = reinterpret_cast<float *>(dead + kChunkWords), *ky1 = kx1 + max_det, *kx2 = ky1 + max_det, *ky2 = kx2 + max_det,
-          *kar = ky2 + max_det;
-    int *ctl = reinterpret_cast<int *>(kar + max_det);                                       // [0] kept so far, [1] kept before chunk
-    int *newkeep = ctl + 2;                                                                  // [kChunk] chunk-local indices kept
+    unsigned long long *mask = reinterpret_cast<unsigned long long *>(car + kChunk);       // [survivors][words]
+    const int kcap = (max_det + 3) & ~3;                                                     // kept list padded to the unroll of the check loop
+    float4 *kbox = reinterpret_cast<float4 *>(mask + (size_t)kChunk * kChunkWords);          // [kcap] (x1, y1, x2, y2) with class offset
+    float *kar = reinterpret_cast<float *>(kbox + kcap);                                     // [kcap] areas
+    int *ctl = reinterpret_cast<int *>(kar + kcap);                                          // [0] kept so far, [1] new keeps of the chunk
+    int *newkeep = ctl + 2;                                                                  // [kChunk] survivor indices kept
+    int *sidx = newkeep + kChunk;                                                            // [kChunk] survivor -> position in the chunk
+    int *wcnt = sidx + kChunk;                                                               // [kChunk / 32] survivors per warp
 
-    const int b = blockIdx.x, tid = threadIdx.x;
+    const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n = min(counts[b], max_nms);
     const float *R = rows + (size_t)b * cap * 6;
     const uint32_t *O = order + (size_t)b * cap;
     float *outb = out + (size_t)b * max_det * 6;
     if (tid == 0) { ctl[0] = 0; ctl[1] = 0; }
+    for (int k = tid; k < kcap; k += kChunk) {                   // padding entries never intersect anything (inter == 0 -> not suppressed)
+        kbox[k] = make_float4(3.0e38f, 3.0e38f, 3.0e38f, 3.0e38f);
+        kar[k] = 0.0f;
+    }
     __syncthreads();
 
     for (int c0 = 0; c0 < n; c0 += kChunk) {
         const int cs = min(kChunk, n - c0);
         const int kept0 = ctl[0];
         if (kept0 >= max_det) break;
-        // ---- load my box (class offset added in fp32 BEFORE the IoU, general.py:1027-1028) ----
-        uint32_t ridx = 0;
-        bool is_dead = true;
+        // ---- my box (class offset added in fp32 BEFORE the IoU, general.py:1027-1028); suppressed by an earlier keep? ----
+        bool alive = false;
         float x1 = 0, y1 = 0, x2 = 0, y2 = 0, ar = 0;
         if (tid < cs) {
-            ridx = O[c0 + tid];
-            const float *r = R + (size_t)ridx * 6;
+            const float *r = R + (size_t)O[c0 + tid] * 6;
             const float off = agnostic ? __fmul_rn(r[5], 0.0f) : __fmul_rn(r[5], kMaxWh);
             x1 = __fadd_rn(r[0], off); y1 = __fadd_rn(r[1], off); x2 = __fadd_rn(r[2], off); y2 = __fadd_rn(r[3], off);
             ar = __fmul_rn(__fsub_rn(x2, x1), __fsub_rn(y2, y1));
-            cx1[tid] = x1; cy1[tid] = y1; cx2[tid] = x2; cy2[tid] = y2; car[tid] = ar;
-            is_dead = false;
-            for (int k = 0; k < kept0; ++k)                                   // suppressed by an earlier keep?
-                if (iou_gt(kx1[k], ky1[k], kx2[k], ky2[k], kar[k], x1, y1, x2, y2, ar, iou_thr)) { is_dead = true; break; }
+            alive = true;
+            for (int k = 0; k < kept0; k += 4) {                 // four independent tests per trip (the loop is latency bound)
+                bool sup = false;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float4 kb = kbox[k + u];
+                    sup |= (k + u < kept0) & iou_gt(kb.x, kb.y, kb.z, kb.w, kar[k + u], x1, y1, x2, y2, ar, iou_thr);
+                }
+                if (sup) { alive = false; break; }
+            }
         }
-        const uint32_t dm = __ballot_sync(0xffffffffu, is_dead);
-        if ((tid & 31) == 0) reinterpret_cast<uint32_t *>(dead)[tid >> 5] = dm;
+        // ---- compact the survivors (order preserved): only they can be kept or suppress anything from here on ----
+        const uint32_t am = __ballot_sync(0xffffffffu, alive);
+        if (lane == 0) wcnt[warp] = __popc(am);
         __syncthreads();
-        // ---- chunk mask: mask[i][w] bit j = box i suppresses box (64w + j), only j > i matters ----
-        for (int e = tid; e < cs * kChunkWords; e += kChunk) {
-            const int i = e / kChunkWords, w = e - i * kChunkWords;
+        int base = 0, S = 0;
+#pragma unroll
+        for (int w = 0; w < kChunk / 32; ++w) {
+            const int c = wcnt[w];
+            if (w < warp) base += c;
+            S += c;
+        }
+        if (alive) {
+            const int ci = base + __popc(am & ((1u << lane) - 1));
+            cx1[ci] = x1; cy1[ci] = y1; cx2[ci] = x2; cy2[ci] = y2; car[ci] = ar;
+            sidx[ci] = tid;
+        }
+        __syncthreads();
+        const int words = (S + 63) >> 6;
+        // ---- survivor mask: mask[i][w] bit j = survivor i suppresses survivor (64w + j), only j > i matters ----
+        for (int e = tid; e < S * words; e += kChunk) {
+            const int i = e / words, w = e - i * words;
             unsigned long long bits = 0;
-            const bool i_dead = (dead[i >> 6] >> (i & 63)) & 1ull;
-            if (!i_dead && 64 * w + 63 > i) {
+            if (64 * w + 63 > i) {
                 const float ax1 = cx1[i], ay1 = cy1[i], ax2 = cx2[i], ay2 = cy2[i], aa = car[i];
-                const int j0 = max(64 * w, i + 1), j1 = min(64 * w + 64, cs);
+                const int j0 = max(64 * w, i + 1), j1 = min(64 * w + 64, S);
                 for (int j = j0; j < j1; ++j)
                     if (iou_gt(ax1, ay1, ax2, ay2, aa, cx1[j], cy1[j], cx2[j], cy2[j], car[j], iou_thr)) bits |= 1ull << (j & 63);
             }
-            mask[(size_t)i * kChunkWords + w] = bits;
+            mask[(size_t)i * words + w] = bits;
         }
         __syncthreads();
-        // ---- deterministic serial keep-scan (one thread; <= kChunk steps, early exit at max_det) ----
-        if (tid == 0) {
+        // ---- deterministic keep-scan by one warp: lane w owns word w of the dead set; <= S steps, early exit at max_det ----
+        if (warp == 0) {
+            unsigned long long myd = ~0ull;
+            if (lane < words) myd = (64 * lane + 64 <= S) ? 0ull : ~((1ull << (S - 64 * lane)) - 1ull);
             int kept = kept0, nk = 0;
-            for (int w = 0; w < kChunkWords && kept < max_det; ++w) {
-                while (kept < max_det) {
-                    const unsigned long long avail = ~dead[w];        // bits >= cs are dead from the load phase
-                    if (!avail) break;
-                    const int bit = __ffsll((long long)avail) - 1, i = 64 * w + bit;
-                    newkeep[nk++] = i;
-                    ++kept;
-                    dead[w] |= 1ull << bit;                            // consumed
-                    const unsigned long long *m = mask + (size_t)i * kChunkWords;
-                    for (int w2 = w; w2 < kChunkWords; ++w2) dead[w2] |= m[w2];
-                }
+            while (kept < max_det) {
+                const uint32_t has = __ballot_sync(0xffffffffu, ~myd != 0ull);
+                if (!has) break;
+                const int wl = __ffs(has) - 1;
+                const unsigned long long dw = __shfl_sync(0xffffffffu, myd, wl);
+                const int bit = __ffsll((long long)~dw) - 1, i = 64 * wl + bit;
+                if (lane == 0) newkeep[nk] = i;
+                ++nk; ++kept;
+                unsigned long long m = (lane < words && lane >= wl) ? mask[(size_t)i * words + lane] : 0ull;
+                if (lane == wl) m |= 1ull << bit;                  // consumed
+                myd |= m;
             }
-            ctl[1] = kept0;
-            ctl[0] = kept;
+            if (lane == 0) { ctl[0] = kept; ctl[1] = nk; }
         }
         __syncthreads();
         // ---- publish the new keeps: kept-box list (for later chunks) and output rows (un-offset boxes, general.py:1040) ----
-        const int nk = ctl[0] - kept0;
+        const int nk = ctl[1];
         for (int t = tid; t < nk; t += kChunk) {
             const int i = newkeep[t], slot = kept0 + t;
-            kx1[slot] = cx1[i]; ky1[slot] = cy1[i]; kx2[slot] = cx2[i]; ky2[slot] = cy2[i]; kar[slot] = car[i];
-            const float *r = R + (size_t)O[c0 + i] * 6;
+            kbox[slot] = make_float4(cx1[i], cy1[i], cx2[i], cy2[i]); kar[slot] = car[i];
+            const float *r = R + (size_t)O[c0 + sidx[i]] * 6;
             float *o = outb + (size_t)slot * 6;
 #pragma unroll
             for (int q = 0; q < 6; ++q) o[q] = r[q];
@@ -401,8 +426,8 @@ int nms_run(const float *pred, int B, int N, int nc, float conf, double iou, con
         uint32_t *t = k0; k0 = k1; k1 = t;
         t = i0; i0 = i1; i1 = t;
     }
-    const size_t smem = (size_t)5 * kChunk * 4 + (size_t)kChunk * kChunkWords * 8 + kChunkWords * 8 + (size_t)5 * max_det * 4 +
-                        2 * 4 + (size_t)kChunk * 4;
+    const size_t smem = (size_t)5 * kChunk * 4 + (size_t)kChunk * kChunkWords * 8 + (size_t)5 * ((max_det + 3) & ~3) * 4 + 2 * 4 +
+                        (size_t)2 * kChunk * 4 + (kChunk / 32) * 4;
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
