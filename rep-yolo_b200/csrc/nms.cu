@@ -318,8 +318,11 @@ __global__ void __launch_bounds__(kChunk) nms_scan_kernel(const float *__restric
         __syncthreads();
         const int words = (S + 63) >> 6;
         // ---- survivor mask: mask[i][w] bit j = survivor i suppresses survivor (64w + j), only j > i matters ----
+        // (work item = (word w, survivor i) with i fastest: the lanes of a warp test the SAME box j against their own box i, so
+        //  the shared-memory reads of j are broadcasts instead of an 8-way bank conflict between words)
         for (int e = tid; e < S * words; e += kChunk) {
-            const int i = e / words, w = e - i * words;
+            const int w = e / S, r = e - w * S;
+            const int i = (w & 1) ? S - 1 - r : r;            // alternate directions: a thread's rows of the triangle add up evenly
             unsigned long long bits = 0;
             if (64 * w + 63 > i) {
                 const float ax1 = cx1[i], ay1 = cy1[i], ax2 = cx2[i], ay2 = cy2[i], aa = car[i];
@@ -330,21 +333,23 @@ __global__ void __launch_bounds__(kChunk) nms_scan_kernel(const float *__restric
             mask[(size_t)i * words + w] = bits;
         }
         __syncthreads();
-        // ---- deterministic keep-scan by one warp: lane w owns word w of the dead set; <= S steps, early exit at max_det ----
+        // ---- deterministic keep-scan by one warp: lane l owns 32-bit word l of the dead set (S <= 512: 16 words); one step =
+        //      local find-first-set, a warp min-reduction, one broadcast row read; <= S steps, early exit at max_det ----
         if (warp == 0) {
-            unsigned long long myd = ~0ull;
-            if (lane < words) myd = (64 * lane + 64 <= S) ? 0ull : ~((1ull << (S - 64 * lane)) - 1ull);
+            const uint32_t *mask32 = reinterpret_cast<const uint32_t *>(mask);
+            const int w32 = 2 * words;
+            uint32_t myd = 0xffffffffu;
+            if (lane < w32) myd = (32 * lane + 32 <= S) ? 0u : (32 * lane >= S ? 0xffffffffu : ~((1u << (S - 32 * lane)) - 1u));
             int kept = kept0, nk = 0;
             while (kept < max_det) {
-                const uint32_t has = __ballot_sync(0xffffffffu, ~myd != 0ull);
-                if (!has) break;
-                const int wl = __ffs(has) - 1;
-                const unsigned long long dw = __shfl_sync(0xffffffffu, myd, wl);
-                const int bit = __ffsll((long long)~dw) - 1, i = 64 * wl + bit;
-                if (lane == 0) newkeep[nk] = i;
+                const uint32_t al = ~myd;
+                const uint32_t cand = al ? (uint32_t)(32 * lane + __ffs(al) - 1) : 0x7fffffffu;
+                const uint32_t i = __reduce_min_sync(0xffffffffu, cand);
+                if (i == 0x7fffffffu) break;
+                if (lane == 0) newkeep[nk] = (int)i;
                 ++nk; ++kept;
-                unsigned long long m = (lane < words && lane >= wl) ? mask[(size_t)i * words + lane] : 0ull;
-                if (lane == wl) m |= 1ull << bit;                  // consumed
+                uint32_t m = lane < w32 ? mask32[(size_t)i * w32 + lane] : 0u;
+                if (lane == (int)(i >> 5)) m |= 1u << (i & 31);    // consumed
                 myd |= m;
             }
             if (lane == 0) { ctl[0] = kept; ctl[1] = nk; }
