@@ -529,9 +529,10 @@ __global__ void __launch_bounds__(kConvMaxThreads, 1) conv_umma_kernel(const __g
         // ===================== TMA producer (whole warp in uniform control flow, one elected lane issues) ==========
         const bool issuer = ptx::elect_one();
         if (p.b_resident && issuer) {
+            const int nc_res = p.n_ntiles > 1 ? (int)(blockIdx.x % (unsigned)p.n_ntiles) * p.BN : 0;   // the one N tile this CTA works on
             ptx::mbar_expect_tx(bres, (uint32_t)(p.kblocks * p.b_stage_bytes));
             for (int kbi = 0; kbi < p.kblocks; ++kbi)
-                ptx::tma_load_2d(sB + (size_t)kbi * p.b_stage_bytes, p.wmap, bres, kbi * p.kb, 0);
+                ptx::tma_load_2d(sB + (size_t)kbi * p.b_stage_bytes, p.wmap, bres, kbi * p.kb, nc_res);
         }
         int sa = 0, sb = 0;
         uint32_t pha = 0, phb = 0;
@@ -637,7 +638,7 @@ int conv_plan_smem(ConvArgs &a, int max_seg_cols) {
     const long avail = kSmemLimit - fixed;
     const long b_total = (long)a.kblocks * a.b_stage_bytes;
     const int a_per_tile = a.a_mode == A_HALO ? a.cblk : a.kblocks;
-    a.b_resident = (a.n_ntiles == 1 && b_total <= 100 * 1024 && avail - b_total >= 2L * a.a_stage_bytes) ? 1 : 0;
+    a.b_resident = ((a.n_ntiles == 1 || a.n_pinned) && b_total <= 100 * 1024 && avail - b_total >= 2L * a.a_stage_bytes) ? 1 : 0;
     if (a.b_resident) {
         a.b_stages = 0;
         a.a_stages = (int)std::min<long>(8, (avail - b_total) / a.a_stage_bytes);

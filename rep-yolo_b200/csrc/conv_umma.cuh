@@ -85,6 +85,8 @@ struct ConvArgs {
     int bv_bytes;              // shared-memory copy of the per-image vectors of a tile's (up to two) images: 4 groups x 2 x cout_pad fp32
     int n_img;                 // images in the batch (bound of the staged second image)
     int tile_contig;           // 1: every CTA takes one contiguous range of tiles instead of every gridDim-th tile
+    int n_pinned;              // 1: gridDim % n_ntiles == 0 with round-robin tiles, i.e. a CTA only ever sees N tile blockIdx % n_ntiles,
+                               //    whose weights may then stay resident in shared memory
     float *pred, *raw;         // Detect outputs
     int no, na, row_off, rows_total;
     float det_stride;

@@ -447,6 +447,10 @@ int bind_conv(ry_plan *p, Op &op, std::vector<CUtensorMap> &maps) {
     a.bv_bytes = (cp.n_src <= 1 && d.in2.tensor >= 0) ? 4 * 2 * cp.cout_pad * 4 : 0;
     a.n_img = B;
     a.tile_contig = a.bv_bytes ? 1 : 0;
+    {
+        static const bool no_pin = getenv("RY_CONV_NO_PIN") != nullptr;
+        a.n_pinned = (!no_pin && a.n_ntiles > 1 && !a.tile_contig && op.grid % a.n_ntiles == 0) ? 1 : 0;
+    }
     int widths[8], n_widths = 0;
     int max_cols = 64;
     build_segments(a, pieces, n_pieces, max_cols, widths, &n_widths);
