@@ -154,6 +154,21 @@ int ry_nms(const float *pred, int B, int N, int nc, float conf_thres, double iou
            int n_classes, int agnostic, int multi_label, int max_det, int max_nms, float *out, int32_t *counts,
            void *workspace, size_t workspace_bytes, void *stream);
 
+/* ---- the callers either side of the path ----
+ * ry_letterbox_u8  <- letterbox  utils/datasets.py:984-1014 (cv2.resize INTER_LINEAR + copyMakeBorder; the shape arithmetic --
+ *                     new_w/new_h/left/top -- stays on the host, rep-yolo_b200/preproc.py) fused with the BGR->RGB, HWC->CHW
+ *                     packing of LoadImages.__next__ (datasets.py:191-195).  src: uint8 HWC (3 channels) image; dst: uint8
+ *                     [3][H1][W1] planes with the channel order reversed (planar_rgb = 1: one image of the uint8 NCHW batch that
+ *                     ry_forward takes after ry_plan_set_image_dtype(RY_U8)) or HWC in the source order (planar_rgb = 0: what
+ *                     letterbox itself returns).  pad_value3_host: HOST int32[3], per source channel.  Bit-exact with cv2.
+ * ry_scale_coords  <- scale_coords + clip_coords  utils/general.py:319-340 (+ the .round() of detect.py:114 when
+ *                     round_result != 0), in place on n rows of >= 4 fp32 (x1,y1,x2,y2,...), row_stride in elements;
+ *                     count_dev: optional DEVICE int32 row count (e.g. one entry of ry_nms's counts), capped by n_max. */
+int ry_letterbox_u8(const uint8_t *src_hwc, int H0, int W0, int src_row_bytes, uint8_t *dst, int H1, int W1, int new_w, int new_h,
+                    int left, int top, const int32_t *pad_value3_host, int planar_rgb, void *stream);
+int ry_scale_coords(float *coords, const int32_t *count_dev, int n_max, int row_stride, float pad_x, float pad_y, float gain, int w0,
+                    int h0, int round_result, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

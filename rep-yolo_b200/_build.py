@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 SO = os.path.join(CSRC, 'librepyolo_b200.so')
-SOURCES = ['conv_umma.cu', 'conv_chain.cu', 'memops.cu', 'attention.cu', 'nms.cu', 'plan.cu']
+SOURCES = ['conv_umma.cu', 'conv_chain.cu', 'memops.cu', 'attention.cu', 'nms.cu', 'preproc.cu', 'plan.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '-Xcompiler', '-fPIC',
               '--threads', '4']
 

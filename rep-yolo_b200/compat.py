@@ -15,6 +15,7 @@ import torch
 import torch.nn as nn
 
 from .model import Model
+from . import preproc as _preproc
 from .nms import non_max_suppression
 
 
@@ -76,6 +77,20 @@ def install() -> list:
             importlib.import_module(modname)
         except Exception:
             continue
+    ref_general = sys.modules.get('utils.general')
+    if ref_general is not None and hasattr(ref_general, 'scale_coords') and not getattr(ref_general.scale_coords, '_ry_native', False):
+        ref_scale_coords = ref_general.scale_coords
+
+        def scale_coords(img1_shape, coords, img0_shape, ratio_pad=None):
+            # detections (fp32 CUDA tensors, detect.py:114 / test.py:141) go to the native kernel; anything else (host label
+            # arrays of the dataset code) stays with the reference's own function
+            if torch.is_tensor(coords) and coords.is_cuda and coords.dtype == torch.float32 and coords.dim() == 2:
+                return _preproc.scale_coords(img1_shape, coords, img0_shape, ratio_pad)
+            return ref_scale_coords(img1_shape, coords, img0_shape, ratio_pad)
+
+        scale_coords._ry_native = True
+        scale_coords.__module__ = 'repyolo_b200.compat'
+        targets['scale_coords'] = scale_coords
     for modname, mod in list(sys.modules.items()):
         if mod is None or not (modname.split('.')[0] in ('models', 'utils', 'detect', 'test', 'hubconf', '__main__')):
             continue
