@@ -851,7 +851,8 @@ int ry_plan_bind(ry_plan *p, int B, int H, int W, void *workspace, size_t worksp
             if (bind_conv(p, op, maps)) return 1;
         }
         if (op.d.kind == RY_OP_CONV_CHAIN && bind_chain(p, op, maps)) return 1;
-        if (op.d.kind == RY_OP_CRISSCROSS || op.d.kind == RY_OP_VERTICAL || op.d.kind == RY_OP_CA) op.launches = 2;
+        if (op.d.kind == RY_OP_CA) op.launches = 2;                                               // partial sums + finish
+        if (op.d.kind == RY_OP_CRISSCROSS || op.d.kind == RY_OP_VERTICAL) op.launches = 3;         // operand prep + two line passes
     }
     // Detect rows: level -> anchor -> y -> x (models/yolo.py:152, 166)
     int rows = 0;
