@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
     uint8_t *sA = smem, *sB = smem + p.off_b;
     float *sbias = reinterpret_cast<float *>(smem + p.off_bias);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + p.off_bar);
-    uint64_t *fullA = bars, *emptyA = fullA + 8, *tfull = emptyA + 8, *tempty = tfull + 4, *bres = tempty + 4;
+    uint64_t *fullA = bars, *emptyA = fullA + 8, *tfull = emptyA + 8, *tempty = tfull + 8, *bres = tempty + 8;
     uint64_t *afull = bres + 1;              // [2][kChainTeams]: A operand of stage s+1 written by team
     uint64_t *pfull = afull + 2 * kChainTeams;   // [2][kChainTeams]: accumulator of stage s+1 complete
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(pfull + 2 * kChainTeams);
@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < 8; ++s) { ptx::mbar_init(fullA + s, 1); ptx::mbar_init(emptyA + s, 1); }
-        for (int a = 0; a < 4; ++a) { ptx::mbar_init(tfull + a, 1); ptx::mbar_init(tempty + a, 4); }
+        for (int a = 0; a < kChainTeams; ++a) { ptx::mbar_init(tfull + a, 1); ptx::mbar_init(tempty + a, 4); }
         ptx::mbar_init(bres, 1);
         for (int i = 0; i < 2 * kChainTeams; ++i) { ptx::mbar_init(afull + i, 1); ptx::mbar_init(pfull + i, 1); }
         ptx::fence_mbar_init();
@@ -181,8 +181,8 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
         uint32_t pha = 0;
         for (int it = 0; it < n_my; ++it) {
             {
-                const int acc = it & 3;
-                const uint32_t aph = (uint32_t)(it >> 2) & 1u;
+                const int acc = it % kChainTeams;                  // one stage-0 accumulator slot per team
+                const uint32_t aph = (uint32_t)(it / kChainTeams) & 1u;
                 ptx::mbar_wait(tempty + acc, aph ^ 1);
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_u + p.stage[0].tmem_col + acc * p.stage[0].N;
@@ -230,12 +230,12 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
             ptx::mbar_wait(bres, 0);
             ptx::tc_fence_after();
             for (int j = 0; j < n_my; ++j) {
-                const int team = j & (kChainTeams - 1);
+                const int team = j % kChainTeams;
                 const uint32_t ph = (uint32_t)(j / kChainTeams) & 1u;
                 ptx::mbar_wait(afull + (s - 1) * kChainTeams + team, ph);
                 ptx::tc_fence_after();
                 const uint64_t a_desc = a_desc0 + (uint64_t)(team * a_inc);
-                const uint32_t d_tmem = tmem_u + p.stage[s].tmem_col + team * p.stage[s].N;
+                const uint32_t d_tmem = tmem_u + p.stage[s].tmem_col + team * p.post_stride;
                 ptx::umma_bf16_d64_first(d_tmem, a_desc, w_desc, idesc, issue, 0u);
                 if (ks > 1) ptx::umma_bf16_d64<2, 1>(d_tmem, a_desc, w_desc, idesc, issue);
                 if (ks > 2) ptx::umma_bf16_d64<4, 1>(d_tmem, a_desc, w_desc, idesc, issue);
@@ -256,19 +256,19 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
         pdl_wait();
         int it = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
-            if ((it & (kChainTeams - 1)) != team) continue;
+            if (it % kChainTeams != team) continue;
             const Tile tc = tile_of(p, t);
             const uint32_t ph = (uint32_t)(it / kChainTeams) & 1u;
             for (int s = 0; s < p.n_stages; ++s) {
                 const ChainStage &sg = p.stage[s];
                 uint32_t taddr;
                 if (s == 0) {
-                    const int acc = it & 3;
-                    ptx::mbar_wait(tfull + acc, (uint32_t)(it >> 2) & 1u);
+                    const int acc = team;
+                    ptx::mbar_wait(tfull + acc, ph);
                     taddr = tmem_base + sg.tmem_col + acc * sg.N + lane_sel;
                 } else {
                     ptx::mbar_wait(pfull + (s - 1) * kChainTeams + team, ph);
-                    taddr = tmem_base + sg.tmem_col + team * sg.N + lane_sel;
+                    taddr = tmem_base + sg.tmem_col + team * p.post_stride + lane_sel;
                 }
                 ptx::tc_fence_after();
                 if (sg.store) {
@@ -315,7 +315,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
                 ptx::tc_fence_before();
                 if (s == 0) {
                     __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive(tempty + (it & 3));
+                    if (lane == 0) ptx::mbar_arrive(tempty + team);
                 }
                 ptx::fence_proxy_async();
                 ptx::bar_sync(1 + team, 128);
@@ -349,14 +349,16 @@ int chain_plan_smem(ChainArgs &a) {
     a.a_box_bytes = a.halo_w * 18 * rb;
     a.a_stage_bytes = (a.a_box_bytes + 1023) & ~1023;
     a.b_stage_bytes = a.stage[0].N * rb;
-    int cols = 4 * a.stage[0].N;
+    int cols = kChainTeams * a.stage[0].N;
     a.stage[0].tmem_col = 0;
     a.anext_bytes = 0;
     a.stage_buf_bytes = 0;
     a.n_store = 0;
     a.bias_floats = 0;
+    int post_n = 0;
     for (int s = 0; s < a.n_stages; ++s) {
-        if (s > 0) { a.stage[s].tmem_col = cols; cols += kChainTeams * a.stage[s].N; }
+        if (s > 0) { a.stage[s].tmem_col = cols; post_n = std::max(post_n, a.stage[s].N); }   // a team's 1x1 accumulators alias: stage s+1 is
+                                                                                               // issued only after the team has read stage s out
         if (a.stage[s].kb_next) a.anext_bytes = std::max(a.anext_bytes, 128 * a.stage[s].kb_next * 2);
         if (a.stage[s].store) {
             a.stage[s].stg_off = a.stage_buf_bytes;
@@ -366,6 +368,8 @@ int chain_plan_smem(ChainArgs &a) {
         a.stage[s].bias_off = a.bias_floats;
         a.bias_floats += a.stage[s].N;
     }
+    a.post_stride = post_n;
+    cols += kChainTeams * post_n;
     if (cols > 512) return 1;
     a.tmem_cols = 32;
     while (a.tmem_cols < cols) a.tmem_cols <<= 1;

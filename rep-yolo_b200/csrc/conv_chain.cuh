@@ -14,8 +14,8 @@
 
 namespace ry {
 
-constexpr int kChainTeams = 4;
-constexpr int kChainThreads = 64 + 128 * kChainTeams + 64;   // producer, stage-0 MMA issuer, 4 teams x 4 warps, two 1x1-stage MMA issuers
+constexpr int kChainTeams = 5;
+constexpr int kChainThreads = 64 + 128 * kChainTeams + 64;   // producer, stage-0 MMA issuer, kChainTeams x 4 warps, two 1x1-stage MMA issuers
 constexpr int kChainMaxStages = 3;
 
 struct ChainStage {
@@ -26,7 +26,7 @@ struct ChainStage {
     int chan;        // absolute channel offset of the store in its tensor
     int swz;         // staging swizzle mask of the store (7/3/1, 0 = dense rows)
     int kb_next;     // channels per row of the next stage's A operand (32 or 64), 0 = last stage
-    int tmem_col;    // accumulator base column: stage 0 = 4 slots of N, stages 1,2 = one slot of N per team
+    int tmem_col;    // accumulator base column: stage 0 = one slot of N per team; stages 1, 2 share one slot of max(N) per team
     int bias_off;    // float offset into the shared-memory bias array
     int ks;          // stages 1,2: K=16 steps (ceil(previous ncol / 16)); stage 0: K steps per tap
     int stg_off;     // byte offset of this stage's staging tile inside the team's staging area
@@ -51,6 +51,7 @@ struct ChainArgs {
     int n_store;               // number of storing stages
     int bias_floats;
     int tmem_cols;             // power of two >= all accumulator columns
+    int post_stride;           // TMEM columns between the teams' (aliased) 1x1-stage accumulators
     int off_b, off_anext, off_stage, off_bias, off_bar;   // shared-memory byte offsets (from the 1 KiB-aligned base)
     ChainStage stage[kChainMaxStages];
 };
