@@ -364,6 +364,159 @@ __global__ void __launch_bounds__(512, 1) dw5_kernel(const __grid_constant__ Dw5
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Depthwise 5x5 on the tensor cores (mma.sync m16n8k16, bf16 x bf16 -> fp32).  A depthwise conv is a GEMM with a
+// block-diagonal weight matrix: for one group of 8 channels and one pair of horizontal taps (dx, dx+1) of kernel row dy
+//     D[pixel][c] += sum_{k = (tap j, channel c')} A[pixel][k] * B[k][c],   A[pixel][(j, c')] = in[y + dy][x + dx + j][c'],
+//                                                                          B[(j, c')][c]     = w[dy][dx + j][c] * (c' == c)
+// 7/8 of the MACs multiply zeros, which the tensor pipe has room for (a 5x5 depthwise conv is 0.2 % of the model's FLOPs)
+// while the FMA pipe does not: the SIMT version above spends ~40 issue slots per output, this one ~0.4.
+//   unit  = 8 pixels x 2 blocks of R = 5 output rows x 8 channels: MMA rows 0-7 = the pixels of block 0, rows 8-15 = block 1
+//           (ldmatrix addresses make that free), one fp32 accumulator fragment per output row;
+//   step  = one input row s of the (R + 4)-row halo: three ldmatrix.x4 give the A fragments of the tap pairs (0,1) (2,3) (4,-),
+//           each feeds every output row i with 0 <= s - i <= 4 (weights of kernel row s - i): a staged vector is read from
+//           shared memory 3 times instead of 25;
+//   B fragments (5 kernel rows x 3 tap pairs) live in registers for the whole work item.
+// Work items, persistence and the cp.async double buffering are those of the SIMT kernel; the halo is stored as four planes
+// (one per 8-channel vector) so that the 8 rows of an ldmatrix matrix are 128 contiguous bytes.  Weights enter as bf16
+// (like every other conv of the model); bias, activation and accumulation are fp32.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kDwR = 5;                         // output rows per half block
+struct Dw5mArgs {
+    const __nv_bfloat16 *in;
+    __nv_bfloat16 *out;
+    const float *w, *bias;          // [25][C] (tap-major), [C]
+    int in_cs, in_off0, in_off1, out_cs, out_off0, out_off1;
+    int C, half, H, W, act;
+    int TW, strips, swarps;         // tile width (multiple of 8), strips of 8 pixels, warps per channel vector
+    int pitch;                      // halo row pitch in pixels
+    int tiles_x, tiles_y, n_items, stage_bytes, halo_bytes;
+};
+
+__device__ __forceinline__ void dw5m_stage_load(const Dw5mArgs &a, uint32_t base, int item) {
+    const int ncg = a.C >> 5;
+    const int cg = item % ncg; item /= ncg;
+    const int tx = item % a.tiles_x; item /= a.tiles_x;
+    const int ty = item % a.tiles_y;
+    const int b = item / a.tiles_y;
+    const int tw4 = a.TW + 4, th4 = 2 * kDwR + 4;
+    const int x0 = tx * a.TW - 2, y0 = ty * 2 * kDwR - 2, c0 = cg * 32;
+    // chunk index = (row py, pixel px, vector v) with v fastest; blockDim and the chunks per row are multiples of 4, so a thread
+    // keeps its v (and its channel offset) for the whole item and walks (py, px) without a division
+    const int v = threadIdx.x & 3;
+    const int c = c0 + v * 8;
+    const int ci = c < a.half ? a.in_off0 + c : a.in_off1 + (c - a.half);
+    const __nv_bfloat16 *src0 = a.in + (size_t)b * a.H * a.W * a.in_cs + ci;
+    const uint32_t dst0 = base + (uint32_t)(v * th4 * a.pitch * 16);
+    const int row_chunks = tw4 * 4;
+    int py = 0, rem = threadIdx.x;
+    while (rem >= row_chunks) { rem -= row_chunks; ++py; }
+    while (py < th4) {
+        const int px = rem >> 2;
+        const int yy = y0 + py, xx = x0 + px;
+        const bool ok = yy >= 0 && yy < a.H && xx >= 0 && xx < a.W;
+        cp_async16(dst0 + (uint32_t)((py * a.pitch + px) * 16), src0 + (ok ? (yy * a.W + xx) * a.in_cs : 0), ok);
+        rem += blockDim.x;
+        while (rem >= row_chunks) { rem -= row_chunks; ++py; }
+    }
+    for (int i = threadIdx.x; i < 25 * 8 + 8; i += blockDim.x) {         // weights [25][32] fp32, then bias [32]
+        const float *src = i < 200 ? a.w + (size_t)(i >> 3) * a.C + c0 + (i & 7) * 4 : a.bias + c0 + (i - 200) * 4;
+        cp_async16(base + (uint32_t)a.halo_bytes + (uint32_t)i * 16, src, true);
+    }
+}
+
+__global__ void __launch_bounds__(128, 4) dw5_mma_kernel(const __grid_constant__ Dw5mArgs a) {
+    pdl_trigger();
+    extern __shared__ __align__(128) uint8_t dw_smem[];
+    const uint32_t smem_u = (uint32_t)__cvta_generic_to_shared(dw_smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, t4 = lane & 3;
+    const int v = warp & 3, sw = warp >> 2;                      // channel vector of this warp, first strip
+    const int ncg = a.C >> 5;
+    const int th4 = 2 * kDwR + 4;
+    // ldmatrix row address of this lane: matrix mi = lane / 8 -> (tap j = mi / 2, half block = mi % 2), row = lane % 8 = pixel
+    const int mi = lane >> 3, mr = lane & 7;
+    const uint32_t lm_off = (uint32_t)((((v * th4) + (mi & 1) * kDwR) * a.pitch + mr) * 16);
+    const int joff = mi >> 1;                                    // second tap of the pair; the pair (4, -) re-reads tap 4 (zero weights)
+    pdl_wait();
+    // one work item per CTA, one staging buffer: several CTAs per SM overlap each other's load and compute phases
+    {
+        const int item = blockIdx.x;
+        dw5m_stage_load(a, smem_u, item);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        const int stage = 0;
+        const uint32_t base_u = smem_u + (uint32_t)stage * a.stage_bytes;
+        const float *swt = reinterpret_cast<const float *>(dw_smem + (size_t)stage * a.stage_bytes + a.halo_bytes) + v * 8;
+        // ---- B fragments: column n = g of the block-diagonal tap-pair matrices; k rows 2*t4, 2*t4+1 (tap j = 0) and +8 (tap j = 1) ----
+        uint32_t bf[5][3][2];
+        {
+            const bool lo = g == 2 * t4, hi = g == 2 * t4 + 1;
+#pragma unroll
+            for (int dy = 0; dy < 5; ++dy)
+#pragma unroll
+                for (int p = 0; p < 3; ++p)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const int dx = 2 * p + j;
+                        const float wv = dx < 5 ? swt[(dy * 5 + dx) * 32 + g] : 0.0f;
+                        bf[dy][p][j] = pack_bf16x2(lo ? wv : 0.0f, hi ? wv : 0.0f);
+                    }
+        }
+        const float bias0 = swt[25 * 32 + 2 * t4], bias1 = swt[25 * 32 + 2 * t4 + 1];
+        int it = item;
+        const int cg = it % ncg; it /= ncg;
+        const int tx = it % a.tiles_x; it /= a.tiles_x;
+        const int ty = it % a.tiles_y;
+        const int b = it / a.tiles_y;
+        for (int s8 = sw; s8 < a.strips; s8 += a.swarps) {       // strips of 8 pixels
+            float acc[kDwR][4];
+#pragma unroll
+            for (int i = 0; i < kDwR; ++i) { acc[i][0] = acc[i][2] = bias0; acc[i][1] = acc[i][3] = bias1; }
+            const uint32_t a_base = base_u + lm_off + (uint32_t)(s8 * 8 * 16);
+#pragma unroll
+            for (int s = 0; s < kDwR + 4; ++s) {                 // input rows of the halo
+                uint32_t af[3][4];
+#pragma unroll
+                for (int p = 0; p < 3; ++p) {
+                    const uint32_t addr = a_base + (uint32_t)((s * a.pitch + (p < 2 ? 2 * p + joff : 4)) * 16);
+                    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                                 : "=r"(af[p][0]), "=r"(af[p][1]), "=r"(af[p][2]), "=r"(af[p][3]) : "r"(addr));
+                }
+#pragma unroll
+                for (int i = 0; i < kDwR; ++i) {
+                    const int dy = s - i;
+                    if (dy < 0 || dy > 4) continue;
+#pragma unroll
+                    for (int p = 0; p < 3; ++p)
+                        mma_bf16_16816(acc[i], af[p][0], af[p][1], af[p][2], af[p][3], bf[dy][p][0], bf[dy][p][1]);
+                }
+            }
+            // ---- epilogue: activation, bf16, 4-byte stores (the 4 lanes of a pixel write 16 contiguous bytes) ----
+            const int x = tx * a.TW + s8 * 8 + g;
+            const int c = cg * 32 + v * 8 + 2 * t4;
+            const int co = c < a.half ? a.out_off0 + c : a.out_off1 + (c - a.half);
+            if (x < a.W) {
+#pragma unroll
+                for (int hb = 0; hb < 2; ++hb)
+#pragma unroll
+                    for (int i = 0; i < kDwR; ++i) {
+                        const int y = ty * 2 * kDwR + hb * kDwR + i;
+                        if (y >= a.H) continue;
+                        float f0 = acc[i][2 * hb], f1 = acc[i][2 * hb + 1];
+                        if (a.act == 1) {                        // SiLU(x) = h + h * tanh(h), h = x / 2
+                            const float h0 = 0.5f * f0, h1 = 0.5f * f1;
+                            f0 = fmaf(h0, tanh_approx_f(h0), h0);
+                            f1 = fmaf(h1, tanh_approx_f(h1), h1);
+                        }
+                        *reinterpret_cast<uint32_t *>(a.out + (((size_t)b * a.H + y) * a.W + x) * a.out_cs + co) = pack_bf16x2(f0, f1);
+                    }
+            }
+        }
+    }
+}
+
 // MP (reference models/common.py:32-38): MaxPool2d(2, 2).  One thread = 8 channels of one output pixel.
 __global__ void __launch_bounds__(256) maxpool2_kernel(const __nv_bfloat16 *__restrict__ in, int in_cs, int in_off,
                                                        __nv_bfloat16 *__restrict__ out, int out_cs, int out_off, int C,
@@ -556,6 +709,31 @@ int stem_launch(const void *img, int img_u8, const float *w27, const float *bias
 void dw5_launch(const __nv_bfloat16 *in, int in_cs, int in_off0, int in_off1, __nv_bfloat16 *out, int out_cs, int out_off0,
                 int out_off1, const float *w, const float *bias, int C, int half, int B, int H, int W, int act,
                 cudaStream_t st) {
+    static const bool use_ffma = getenv("RY_DW5_FFMA") != nullptr;
+    if (!use_ffma && half % 8 == 0) {
+        Dw5mArgs m = {};
+        m.in = in; m.out = out; m.w = w; m.bias = bias;
+        m.in_cs = in_cs; m.in_off0 = in_off0; m.in_off1 = in_off1; m.out_cs = out_cs; m.out_off0 = out_off0; m.out_off1 = out_off1;
+        m.C = C; m.half = half; m.H = H; m.W = W; m.act = act;
+        const int w8 = (W + 7) / 8 * 8;
+        m.TW = std::min(w8, 40);
+        if (w8 > 40 && w8 % 40 != 0 && w8 % 32 == 0) m.TW = 32;
+        m.strips = m.TW / 8;
+        m.swarps = 1;                                            // 4 warps (one per channel vector), every warp walks all strips
+        m.pitch = m.TW + 4;
+        m.tiles_x = cdiv(W, m.TW); m.tiles_y = cdiv(H, 2 * kDwR);
+        m.halo_bytes = 4 * (2 * kDwR + 4) * m.pitch * 16;
+        m.stage_bytes = (m.halo_bytes + 208 * 16 + 127) & ~127;
+        m.n_items = B * m.tiles_y * m.tiles_x * (C / 32);
+        const int threads = 128 * m.swarps;
+        static bool attr_m = false;
+        if (!attr_m) {
+            cudaFuncSetAttribute(dw5_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            attr_m = true;
+        }
+        launch_pdl(dw5_mma_kernel, dim3(m.n_items), dim3(threads), (size_t)m.stage_bytes, st, m);
+        return;
+    }
     // tile = (4 SX) x (8 RG) pixels, SX * RG warps.  Model: an SM issues for ~16 warps at a time, so one round of n resident
     // CTAs costs n * warps; rounds = ceil(items / (148 n)); staged halo pixels per output pixel add L2 -> smem traffic.
     Dw5Args a = {};
