@@ -7,6 +7,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace ry {
 
@@ -391,6 +392,7 @@ struct Dw5mArgs {
     int TW, strips, swarps;         // tile width (multiple of 8), strips of 8 pixels, warps per channel vector
     int pitch;                      // halo row pitch in pixels
     int tiles_x, tiles_y, n_items, stage_bytes, halo_bytes;
+    const CUtensorMap *imap;        // input map {C, W, H, B}, box {8, TW + 4, 2R + 4, 1}: one TMA load per channel vector (OOB = zero padding)
 };
 
 __device__ __forceinline__ void dw5m_stage_load(const Dw5mArgs &a, uint32_t base, int item) {
@@ -442,10 +444,43 @@ __global__ void __launch_bounds__(128, 4) dw5_mma_kernel(const __grid_constant__
     // one work item per CTA, one staging buffer: several CTAs per SM overlap each other's load and compute phases
     {
         const int item = blockIdx.x;
-        dw5m_stage_load(a, smem_u, item);
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncthreads();
+        uint64_t *bar = reinterpret_cast<uint64_t *>(dw_smem + a.stage_bytes);
+        if (a.imap != nullptr) {
+            // halo planes by TMA (four boxes of 8 channels; out-of-bounds pixels arrive as zeros = the conv padding)
+            if (threadIdx.x == 0) {
+                ptx::mbar_init(bar, 1);
+                ptx::fence_mbar_init();
+                int it = item;
+                const int cg = it % ncg; it /= ncg;
+                const int tx = it % a.tiles_x; it /= a.tiles_x;
+                const int ty = it % a.tiles_y;
+                const int b = it / a.tiles_y;
+                const uint32_t plane = (uint32_t)(th4 * a.pitch * 16);
+                ptx::mbar_expect_tx(bar, 4u * plane);
+#pragma unroll
+                for (int vv = 0; vv < 4; ++vv) {
+                    const int c = cg * 32 + vv * 8;
+                    const int ci = c < a.half ? a.in_off0 + c : a.in_off1 + (c - a.half);
+                    ptx::tma_load_4d(dw_smem + (size_t)vv * plane, a.imap, bar, ci, tx * a.TW - 2, ty * 2 * kDwR - 2, b);
+                }
+            }
+            {
+                const int c0 = (item % ncg) * 32;
+                for (int i = threadIdx.x; i < 25 * 8 + 8; i += blockDim.x) {         // weights [25][32] fp32, then bias [32]
+                    const float *src = i < 200 ? a.w + (size_t)(i >> 3) * a.C + c0 + (i & 7) * 4 : a.bias + c0 + (i - 200) * 4;
+                    cp_async16(smem_u + (uint32_t)a.halo_bytes + (uint32_t)i * 16, src, true);
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncthreads();                                      // barrier initialised + weights visible
+            ptx::mbar_wait(bar, 0);
+        } else {
+            dw5m_stage_load(a, smem_u, item);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncthreads();
+        }
         const int stage = 0;
         const uint32_t base_u = smem_u + (uint32_t)stage * a.stage_bytes;
         const float *swt = reinterpret_cast<const float *>(dw_smem + (size_t)stage * a.stage_bytes + a.halo_bytes) + v * 8;
@@ -706,18 +741,25 @@ int stem_launch(const void *img, int img_u8, const float *w27, const float *bias
     return 0;
 }
 
+int dw5_tile_w(int W) {
+    const int w8 = (W + 7) / 8 * 8;
+    int tw = std::min(w8, 40);
+    if (w8 > 40 && w8 % 40 != 0 && w8 % 32 == 0) tw = 32;
+    return tw;
+}
+int dw5_halo_rows() { return 2 * kDwR + 4; }
+
 void dw5_launch(const __nv_bfloat16 *in, int in_cs, int in_off0, int in_off1, __nv_bfloat16 *out, int out_cs, int out_off0,
                 int out_off1, const float *w, const float *bias, int C, int half, int B, int H, int W, int act,
-                cudaStream_t st) {
+                const CUtensorMap *imap, cudaStream_t st) {
     static const bool use_ffma = getenv("RY_DW5_FFMA") != nullptr;
     if (!use_ffma && half % 8 == 0) {
         Dw5mArgs m = {};
         m.in = in; m.out = out; m.w = w; m.bias = bias;
         m.in_cs = in_cs; m.in_off0 = in_off0; m.in_off1 = in_off1; m.out_cs = out_cs; m.out_off0 = out_off0; m.out_off1 = out_off1;
         m.C = C; m.half = half; m.H = H; m.W = W; m.act = act;
-        const int w8 = (W + 7) / 8 * 8;
-        m.TW = std::min(w8, 40);
-        if (w8 > 40 && w8 % 40 != 0 && w8 % 32 == 0) m.TW = 32;
+        m.TW = dw5_tile_w(W);
+        m.imap = imap;
         m.strips = m.TW / 8;
         m.swarps = 1;                                            // 4 warps (one per channel vector), every warp walks all strips
         m.pitch = m.TW + 4;
@@ -731,7 +773,7 @@ void dw5_launch(const __nv_bfloat16 *in, int in_cs, int in_off0, int in_off1, __
             cudaFuncSetAttribute(dw5_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
             attr_m = true;
         }
-        launch_pdl(dw5_mma_kernel, dim3(m.n_items), dim3(threads), (size_t)m.stage_bytes, st, m);
+        launch_pdl(dw5_mma_kernel, dim3(m.n_items), dim3(threads), (size_t)m.stage_bytes + 16, st, m);   // + the TMA barrier
         return;
     }
     // tile = (4 SX) x (8 RG) pixels, SX * RG warps.  Model: an SM issues for ~16 warps at a time, so one round of n resident

@@ -1,5 +1,6 @@
 // Launchers of the memory-bound kernels (memops.cu) and the attention kernels (attention.cu).
 #pragma once
+#include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
@@ -7,9 +8,13 @@ namespace ry {
 
 int stem_launch(const void *img, int img_u8, const float *w27, const float *bias, __nv_bfloat16 *out, int out_cs, int out_off,
                 int cout, int B, int H, int W, cudaStream_t st);
+// imap: optional tensor map of the input tensor {C, W, H, B} with box {8, dw5_tile_w(W) + 4, dw5_halo_rows(), 1}, no swizzle
+// (the halo planes are then fetched by TMA); NULL = per-thread cp.async staging
 void dw5_launch(const __nv_bfloat16 *in, int in_cs, int in_off0, int in_off1, __nv_bfloat16 *out, int out_cs, int out_off0,
                 int out_off1, const float *w, const float *bias, int C, int half, int B, int H, int W, int act,
-                cudaStream_t st);
+                const CUtensorMap *imap, cudaStream_t st);
+int dw5_tile_w(int W);
+int dw5_halo_rows();
 void maxpool2_launch(const __nv_bfloat16 *in, int in_cs, int in_off, __nv_bfloat16 *out, int out_cs, int out_off, int C,
                      int B, int H, int W, cudaStream_t st);
 void spp_launch(const __nv_bfloat16 *in, int in_cs, int in_off, __nv_bfloat16 *out, int out_cs, int off5, int off9,

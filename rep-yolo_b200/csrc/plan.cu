@@ -627,7 +627,7 @@ int run_op(ry_plan *p, Op &op, const float *image, float *pred, float *raws[3], 
             const int half = split ? d.in0.c_len : C;
             dw5_launch(bf(p, d.in0.tensor), ti.d.channels, d.in0.c_off, split ? d.in1.c_off : 0, bf(p, d.out0.tensor),
                        to.d.channels, d.out0.c_off, split ? d.out1.c_off : 0, wf(p, op.dev[0]), wf(p, op.dev[1]), C, half, B,
-                       ti.h, ti.w, d.act, st);
+                       ti.h, ti.w, d.act, op.tmap_first >= 0 ? p->d_tmaps + op.tmap_first : nullptr, st);
             break;
         }
         case RY_OP_MAXPOOL2: {
@@ -851,6 +851,18 @@ int ry_plan_bind(ry_plan *p, int B, int H, int W, void *workspace, size_t worksp
             if (bind_conv(p, op, maps)) return 1;
         }
         if (op.d.kind == RY_OP_CONV_CHAIN && bind_chain(p, op, maps)) return 1;
+        if (op.d.kind == RY_OP_DW5) {
+            // input tensor as {C, W, H, B}; one box = 8 channels x the halo of a tile (dw5_mma_kernel)
+            const Tensor &ti = p->tensors[op.d.in0.tensor];
+            const cuuint64_t cs = (cuuint64_t)ti.d.channels;
+            const cuuint64_t dims[4] = {cs, (cuuint64_t)ti.w, (cuuint64_t)ti.h, (cuuint64_t)B};
+            const cuuint64_t str[3] = {cs * 2, (cuuint64_t)ti.w * cs * 2, (cuuint64_t)ti.h * ti.w * cs * 2};
+            const cuuint32_t box[4] = {8, (cuuint32_t)(dw5_tile_w(ti.w) + 4), (cuuint32_t)dw5_halo_rows(), 1};
+            CUtensorMap m;
+            op.tmap_first = (int)maps.size();
+            if (encode_map(&m, bf(p, op.d.in0.tensor), 4, dims, str, box, 8, false)) return 1;
+            maps.push_back(m);
+        }
         if (op.d.kind == RY_OP_CA) op.launches = 2;                                               // partial sums + finish
         if (op.d.kind == RY_OP_CRISSCROSS || op.d.kind == RY_OP_VERTICAL) op.launches = 3;         // operand prep + two line passes
     }
