@@ -21,3 +21,8 @@ $PROF > gpurun_out/plain2_$TAG.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:$KRE -s $SKIP -c 3 -f -o gpurun_out/prof_$TAG $PROF > gpurun_out/ncu_full_$TAG.log 2>&1
 echo "ncu full rc=$?"
 tail -3 gpurun_out/gputests_$TAG.log
+# DRAM traffic of every conv launch of ONE forward pass (the third: two warm-up passes are skipped) -> tools/conv_traffic.py
+NCONV=${4:-109}
+ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:"conv_umma_kernel|conv_chain_kernel" \
+    -s $((2 * NCONV)) -c $NCONV --csv --log-file gpurun_out/conv_traffic_$TAG.csv $PROF > gpurun_out/ncu_traffic_$TAG.log 2>&1
+echo "ncu conv traffic rc=$?"
