@@ -821,7 +821,8 @@ void maxpool2_launch(const __nv_bfloat16 *in, int in_cs, int in_off, __nv_bfloat
 
 void spp_launch(const __nv_bfloat16 *in, int in_cs, int in_off, __nv_bfloat16 *out, int out_cs, int off5, int off9,
                 int off13, int C, int B, int H, int W, cudaStream_t st) {
-    int CH = 64;
+    static const int ch0 = getenv("RY_SPP_CH") ? atoi(getenv("RY_SPP_CH")) : 32;   // channels per CTA: 32 -> 51 KB of planes at 20x20, 4 CTAs per SM
+    int CH = ch0;
     while (CH > 8 && (C % CH != 0 || (size_t)2 * H * W * CH * 2 > 200 * 1024)) CH -= 8;
     const size_t smem = (size_t)2 * H * W * CH * 2;
     static bool attr_set = false;
