@@ -1,6 +1,6 @@
 // Implicit-GEMM convolution (1x1, 3x3 s1/s2) for NHWC bf16 activations on the 5th-gen tensor cores.
 //   D[pixel, cout] = sum_{tap, cin} A[pixel + tap, cin] * W[cout, tap, cin]
-// One persistent CTA per SM, 10 warps: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer, warps 2..9 = epilogue.
+// One persistent CTA per SM: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer, warps 2..9 (or 2..17) = epilogue.
 //
 // A operand (activations), two fetch modes:
 //   A_BOX   one TMA box per (tap, K block): [tn][th][tw] pixels x kb channels, shifted by the tap, zero fill outside the
@@ -17,8 +17,14 @@
 //
 // Epilogue: TMEM -> registers -> +bias, SiLU (0.5x(1+tanh(0.5x)), one MUFU), residual / per-image vector add -> bf16 ->
 // swizzled shared-memory staging -> TMA store into a channel range of the NHWC output (concat slots, GSConv shuffle
-// halves).  Two column groups of four warps work on disjoint accumulator columns.  The Detect head (mode 1) decodes in
-// registers and writes pred / raw rows directly.
+// halves).  N <= 128 (4 x N TMEM columns fit): four 4-warp teams take alternate tiles; wider N tiles: two column groups of
+// four warps on disjoint accumulator columns.  HBM-bound 256-wide 1x1 layers are therefore run as two 128-wide N tiles;
+// with round-robin tiles and gridDim % n_ntiles == 0 a CTA only ever sees one N tile, whose weights then stay resident.
+// Optional fused MaxPool2d(2,2) (1x1 conv + the MP that follows a DER_Block): 2-D even pixel tiles, the 2x2 max is taken
+// from the staged tile and only the pooled tile is stored.  Residual / per-image vector operands are fetched one step
+// ahead; the per-image vector is staged in shared memory per image (those convs walk contiguous tile ranges).
+// The Detect head (mode 1): the eight epilogue warps split the head columns, decode in registers, stage
+// [anchor][pixel][no] records in shared memory and write them as contiguous 16-byte vectors.
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
