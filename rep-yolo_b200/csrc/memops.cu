@@ -559,15 +559,14 @@ __global__ void __launch_bounds__(256) maxpool2_kernel(const __nv_bfloat16 *__re
     pdl_trigger();
     pdl_wait();
     const int vecs = C / 8, Ho = H / 2, Wo = W / 2;
-    const size_t total = (size_t)B * Ho * Wo * vecs;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int v = (int)(i % vecs);
-        const size_t opix = i / vecs;
-        const int xo = (int)(opix % Wo), yo = (int)((opix / Wo) % Ho);
-        const size_t b = opix / ((size_t)Wo * Ho);
-        const __nv_bfloat16 *p = in + ((b * H + 2 * yo) * W + 2 * xo) * in_cs + in_off + v * 8;
+    const unsigned total = (unsigned)B * Ho * Wo * vecs;                 // 32-bit index arithmetic (maps of < 2^31 vectors)
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const unsigned opix = i / vecs, v = i - opix * vecs;
+        const unsigned orow = opix / Wo, xo = opix - orow * Wo;          // orow = b * Ho + yo
+        const unsigned b = orow / Ho, yo = orow - b * Ho;
+        const __nv_bfloat16 *p = in + (((size_t)b * H + 2 * yo) * W + 2 * xo) * in_cs + in_off + v * 8;
         const uint4 a = ldg16(p), c = ldg16(p + in_cs), d = ldg16(p + (size_t)W * in_cs), e = ldg16(p + (size_t)(W + 1) * in_cs);
-        stg16(out + opix * out_cs + out_off + v * 8, bf16x8_max(bf16x8_max(a, c), bf16x8_max(d, e)));
+        stg16(out + (size_t)opix * out_cs + out_off + v * 8, bf16x8_max(bf16x8_max(a, c), bf16x8_max(d, e)));
     }
 }
 
@@ -625,15 +624,18 @@ __global__ void __launch_bounds__(256) upsample2_kernel(const __nv_bfloat16 *__r
                                                         int B, int H, int W) {
     pdl_trigger();
     pdl_wait();
-    const int vecs = C / 8, Ho = H * 2, Wo = W * 2;
-    const size_t total = (size_t)B * Ho * Wo * vecs;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int v = (int)(i % vecs);
-        const size_t opix = i / vecs;
-        const int xo = (int)(opix % Wo), yo = (int)((opix / Wo) % Ho);
-        const size_t b = opix / ((size_t)Wo * Ho);
-        stg16(out + opix * out_cs + out_off + v * 8,
-              ldg16(in + ((b * H + yo / 2) * W + xo / 2) * in_cs + in_off + v * 8));
+    // one thread = one INPUT vector (8 channels of one pixel) -> its four output pixels; 32-bit index arithmetic
+    const int vecs = C / 8, Wo = W * 2;
+    const unsigned total = (unsigned)B * H * W * vecs;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const unsigned ipix = i / vecs, v = i - ipix * vecs;
+        const unsigned row = ipix / W, x = ipix - row * W;        // row = b * H + y
+        const uint4 u = ldg16(in + (size_t)ipix * in_cs + in_off + v * 8);
+        __nv_bfloat16 *o = out + ((size_t)row * 2 * Wo + 2 * x) * out_cs + out_off + v * 8;
+        stg16(o, u);
+        stg16(o + out_cs, u);
+        stg16(o + (size_t)Wo * out_cs, u);
+        stg16(o + (size_t)(Wo + 1) * out_cs, u);
     }
 }
 
@@ -835,7 +837,7 @@ void spp_launch(const __nv_bfloat16 *in, int in_cs, int in_off, __nv_bfloat16 *o
 
 void upsample2_launch(const __nv_bfloat16 *in, int in_cs, int in_off, __nv_bfloat16 *out, int out_cs, int out_off, int C,
                       int B, int H, int W, cudaStream_t st) {
-    const size_t total = (size_t)B * (2 * H) * (2 * W) * (C / 8);
+    const size_t total = (size_t)B * H * W * (C / 8);
     launch_pdl(upsample2_kernel, dim3(grid_for(total, 256)), dim3(256), 0, st, in, in_cs, in_off, out, out_cs, out_off, C, B, H, W);
 }
 
