@@ -43,6 +43,9 @@ __device__ __forceinline__ void mma_bf16_16816(float *c, uint32_t a0, uint32_t a
 constexpr int kStemLines = 3 * (2 * kStemTH + 1);                       // (channel, input row) lines of one patch
 constexpr int kStemPatchFloats = kStemLines * kStemPitch;
 
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, bool ok) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16 : 0) : "memory");   // !ok: zero fill
+}
 __device__ __forceinline__ void cp_async4(uint32_t dst, const float *src, bool ok) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(ok ? 4 : 0) : "memory");   // !ok: zero fill
 }
@@ -56,7 +59,8 @@ __global__ void __launch_bounds__(256) stem_kernel(const void *__restrict__ img_
     pdl_trigger();
     constexpr int NT = COUT / 8;
     constexpr int kElem = U8 ? 1 : 4;                                          // bytes per patch element
-    constexpr int kX0 = U8 ? 3 : 0;                                            // patch column 0 sits at this element offset
+    constexpr int kX0 = 3;                                                     // patch column 0 sits at this element offset: both
+                                                                               // paths fetch ALIGNED words (4 x u8 / 4 x fp32) from column wi0 - 3 on
     extern __shared__ __align__(16) uint8_t stem_smem[];
     uint8_t *patch = stem_smem;                                                // 2 x [lines][pitch] elements, filled by cp.async
     __nv_bfloat16 *stage = reinterpret_cast<__nv_bfloat16 *>(stem_smem + 2 * kStemPatchFloats * kElem);   // [2 rows][64 px][COUT]
@@ -112,10 +116,10 @@ __global__ void __launch_bounds__(256) stem_kernel(const void *__restrict__ img_
             } else {
                 const float *src = static_cast<const float *>(img_v) + row_base;
 #pragma unroll
-                for (int j = 0; j < 5; ++j) {
-                    const int x = lane + 32 * j, xx = wi0 + x;
-                    const bool ok = row_ok && xx >= 0 && xx < W;
-                    if (x < kStemPW) cp_async4(dst + x * 4, src + (ok ? xx : 0), ok);
+                for (int j = 0; j < 2; ++j) {
+                    const int wd = lane + 32 * j, xx = wi0 - 3 + 4 * wd;       // aligned 16-byte word: columns xx .. xx+3 (W % 4 == 0:
+                    const bool ok = row_ok && xx >= 0 && xx < W;                // a word is entirely inside or entirely outside the row)
+                    if (wd < 34) cp_async16(dst + wd * 16, src + (ok ? xx : 0), ok);
                 }
             }
         }
@@ -227,9 +231,6 @@ struct Dw5Args {
     int tiles_x, tiles_y, n_items, stage_bytes, halo_bytes;
 };
 
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, bool ok) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16 : 0) : "memory");   // !ok: zero fill
-}
 __device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
     uint64_t r;
     asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));

@@ -587,6 +587,7 @@ int run_op(ry_plan *p, Op &op, const float *image, float *pred, float *raws[3], 
     switch (d.kind) {
         case RY_OP_STEM: {
             if (!image) RY_FAIL("stem: image pointer is NULL");
+            if (reinterpret_cast<uintptr_t>(image) & (p->image_u8 ? 3 : 15)) RY_FAIL("stem: the image must be 16-byte aligned (4-byte for uint8)");
             const Tensor &to = p->tensors[d.out0.tensor];
             if (stem_launch(image, p->image_u8, wf(p, op.dev[0]), wf(p, op.dev[1]), bf(p, d.out0.tensor), to.d.channels, d.out0.c_off, d.cout, B,
                             p->H, p->W, st))
