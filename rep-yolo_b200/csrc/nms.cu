@@ -231,6 +231,91 @@ __global__ void __launch_bounds__(kSortThreads) sort_scatter_kernel(const uint32
     }
 }
 
+// ---- one-kernel sort for small candidate sets -------------------------------------------------------------------
+// When an image has at most a few tens of thousands of candidates (every single-label configuration: cap = N), the twelve
+// launches of the multi-CTA sort above cost more in launch / drain latency than the sort itself.  Here ONE CTA per image runs
+// all four stable LSD passes over the image's key / index arrays (global memory, a few hundred KB per image: L2 resident):
+// histogram (shared atomics) -> digit bases -> tile-by-tile ordered scatter (same warp-ordered multi-split as above).
+constexpr int kSoloThreads = 1024;
+constexpr int kSoloWarps = kSoloThreads / 32;
+constexpr int kSoloItems = 8;                            // keys per thread per tile
+constexpr int kSoloTile = kSoloThreads * kSoloItems;
+constexpr int kSoloMaxCap = 32768;
+
+__global__ void __launch_bounds__(kSoloThreads) sort_image_kernel(uint32_t *__restrict__ keys0, uint32_t *__restrict__ idx0,
+                                                                   uint32_t *__restrict__ keys1, uint32_t *__restrict__ idx1,
+                                                                   const int *__restrict__ counts, size_t cap) {
+    __shared__ uint32_t cnt[kSoloWarps][256];            // per-warp digit counts of the current tile -> output positions
+    __shared__ uint32_t dbase[256];                      // running output position of each digit
+    __shared__ int warp_sums[32];
+    const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n = min(counts[b], (int)cap);
+    uint32_t *Ka = keys0 + (size_t)b * cap, *Kb = keys1 + (size_t)b * cap;
+    uint32_t *Ia = idx0 + (size_t)b * cap, *Ib = idx1 + (size_t)b * cap;
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 8 * pass;
+        const uint32_t *Ks = (pass & 1) ? Kb : Ka, *Is = (pass & 1) ? Ib : Ia;     // passes ping-pong: a -> b -> a -> b -> a
+        uint32_t *Kd = (pass & 1) ? Ka : Kb, *Id = (pass & 1) ? Ia : Ib;
+        if (tid < 256) dbase[tid] = 0;
+        __syncthreads();
+        for (int i = tid; i < n; i += kSoloThreads) atomicAdd(&dbase[(Ks[i] >> shift) & 255], 1u);
+        __syncthreads();
+        {   // exclusive scan of the 256 digit counts (every thread takes part in the block scan; threads >= 256 add zero)
+            const int c = tid < 256 ? (int)dbase[tid] : 0;
+            int total;
+            const int ex = block_excl_scan(c, warp_sums, &total);
+            if (tid < 256) dbase[tid] = (uint32_t)ex;
+        }
+        __syncthreads();
+        for (int t0 = 0; t0 < n; t0 += kSoloTile) {
+            for (int i = tid; i < kSoloWarps * 256; i += kSoloThreads) (&cnt[0][0])[i] = 0;
+            __syncthreads();
+            const int wstart = t0 + warp * (32 * kSoloItems);    // each warp owns a contiguous run of the tile
+            uint32_t key[kSoloItems], val[kSoloItems], rank[kSoloItems];
+#pragma unroll
+            for (int r = 0; r < kSoloItems; ++r) {
+                const int i = wstart + r * 32 + lane;
+                const bool valid = i < n;
+                const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+                rank[r] = 0; key[r] = 0; val[r] = 0;
+                if (valid) {
+                    key[r] = Ks[i];
+                    val[r] = Is[i];
+                    const uint32_t d = (key[r] >> shift) & 255;
+                    const uint32_t peers = __match_any_sync(vmask, d);
+                    const uint32_t prior = cnt[warp][d];
+                    __syncwarp(vmask);
+                    if ((peers & ((1u << lane) - 1)) == 0) cnt[warp][d] = prior + __popc(peers);   // lowest lane of the group
+                    __syncwarp(vmask);
+                    rank[r] = prior + __popc(peers & ((1u << lane) - 1));
+                }
+            }
+            __syncthreads();
+            if (tid < 256) {                                     // per digit: exclusive prefix over warps + running base
+                uint32_t run = dbase[tid];
+#pragma unroll 8
+                for (int w = 0; w < kSoloWarps; ++w) {
+                    const uint32_t c = cnt[w][tid];
+                    cnt[w][tid] = run;
+                    run += c;
+                }
+                dbase[tid] = run;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int r = 0; r < kSoloItems; ++r) {
+                const int i = wstart + r * 32 + lane;
+                if (i < n) {
+                    const uint32_t pos = cnt[warp][(key[r] >> shift) & 255] + rank[r];
+                    Kd[pos] = key[r];
+                    Id[pos] = val[r];
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
 // ---- greedy scan ---------------------------------------------------------------------------------------------------
 // torchvision's CPU kernel suppresses iff (double)ovr > (double)thr with ovr the fp32 quotient.  For a float q,
 // (double)q > thr  <=>  q >= t_up, t_up = the smallest float whose value exceeds thr (computed on the host), so the
@@ -399,8 +484,9 @@ NmsLayout nms_layout(int B, int N, int nc, int multi_label) {
 size_t nms_workspace_bytes(int B, int N, int nc, int multi_label) { return nms_layout(B, N, nc, multi_label).total; }
 
 int nms_launch_count(int B, int N, int nc, int multi_label) {
-    (void)B; (void)N; (void)nc; (void)multi_label;
-    return 1 + 4 * 3 + 1;
+    (void)B;
+    const size_t cap = (size_t)N * ((multi_label && nc > 1) ? nc : 1);
+    return cap <= (size_t)kSoloMaxCap ? 3 : 1 + 4 * 3 + 1;        // filter, sort (one kernel, or hist / scan / scatter x 4), scan
 }
 
 int nms_run(const float *pred, int B, int N, int nc, float conf, double iou, const int32_t *classes_host, int n_classes,
@@ -422,8 +508,11 @@ int nms_run(const float *pred, int B, int N, int nc, float conf, double iou, con
     if (n_classes > 0) RY_CUDA(cudaMemcpyAsync(cls, classes_host, (size_t)n_classes * 4, cudaMemcpyHostToDevice, st));
 
     nms_filter_kernel<<<B, kFilterThreads, 0, st>>>(pred, N, nc, conf, multi_label, cls, n_classes, L.cap, rows, k0, i0, cnt);
+    static const bool no_solo = getenv("RY_NMS_MULTI_SORT") != nullptr;
+    const bool solo = !no_solo && L.cap <= (size_t)kSoloMaxCap;
+    if (solo) sort_image_kernel<<<B, kSoloThreads, 0, st>>>(k0, i0, k1, i1, cnt, L.cap);      // four passes: the result is back in k0 / i0
     const dim3 sgrid(L.nblk, B);
-    for (int pass = 0; pass < 4; ++pass) {
+    for (int pass = 0; pass < 4 && !solo; ++pass) {
         const int shift = 8 * pass;
         sort_hist_kernel<<<sgrid, kSortThreads, 0, st>>>(k0, cnt, L.cap, shift, L.nblk, hist);
         sort_scan_kernel<<<B, 256, 0, st>>>(hist, L.nblk);
