@@ -32,16 +32,20 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+#ifndef RY_MBAR_HINT
+#define RY_MBAR_HINT 0x989680
+#endif
+constexpr uint32_t kMbarSuspendHint = RY_MBAR_HINT;
 __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n"
         ".reg .pred P;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, P;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n"      // %3: suspend-time hint -- the warp sleeps in hardware
+        "selp.u32 %0, 1, 0, P;\n"                                          // until the phase flips instead of re-issuing the poll
         "}\n"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(kMbarSuspendHint)
         : "memory");
     return ok != 0;
 }
