@@ -9,7 +9,7 @@ SKIP=${3:-0}
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q > gpurun_out/gputests_$TAG.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/gputests_$TAG.log
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke_$TAG.log 2>&1; echo "smoke rc=$?"
-python bench.py --steps 10 --warmup 3 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; echo "bench rc=$?"
+python bench.py --steps 50 --warmup 3 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; echo "bench rc=$?"
 cat gpurun_out/bench_$TAG.json
 python tools/profile_ops.py --out gpurun_out/ops_$TAG.txt > /dev/null 2> gpurun_out/prof_$TAG.err; echo "profile_ops rc=$?"
 BENCH="python bench.py --steps 3 --warmup 3 --no-cpu-baseline"
