@@ -701,7 +701,24 @@ __global__ void __launch_bounds__(256) ca_finish_kernel(const float *__restrict_
     __syncthreads();
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         float s = 0.0f;
-        for (int j = 0; j < Ch; ++j) s = fmaf(__ldg(f2 + (size_t)c * Ch + j), hid[j], s);
+        if ((Ch & 3) == 0) {                                  // the row of f2 as independent 16-byte loads (the loop is L2-latency bound)
+            const float4 *row = reinterpret_cast<const float4 *>(f2 + (size_t)c * Ch);
+            for (int j0 = 0; j0 < Ch; j0 += 32) {
+                float4 w[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) w[q] = j0 + 4 * q < Ch ? __ldg(row + (j0 >> 2) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int j = j0 + 4 * q;
+                    if (j < Ch) {                             // same summation order as the scalar loop
+                        s = fmaf(w[q].x, hid[j], s); s = fmaf(w[q].y, hid[j + 1], s);
+                        s = fmaf(w[q].z, hid[j + 2], s); s = fmaf(w[q].w, hid[j + 3], s);
+                    }
+                }
+            }
+        } else {
+            for (int j = 0; j < Ch; ++j) s = fmaf(__ldg(f2 + (size_t)c * Ch + j), hid[j], s);
+        }
         const float a = 1.0f / (1.0f + __expf(-s));
         out[(size_t)b * out_cs + out_off + c] = mean[c] * a + mean[c];
     }
