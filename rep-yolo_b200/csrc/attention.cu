@@ -415,7 +415,7 @@ int prep_launch(const AttnParams &p, cudaStream_t st) {
     const size_t npix = (size_t)p.B * p.H * p.W;
     const int ppb = kPrepUnroll * kPrepThreads / p.Cq;
     const size_t blocks = (npix + ppb - 1) / ppb;
-    const int grid = (int)std::min<size_t>(blocks, (size_t)kNumSMs * 2);   // resident CTAs: the per-group constants are fetched once
+    const int grid = (int)std::min<size_t>(blocks, (size_t)num_sms() * 2);   // resident CTAs: the per-group constants are fetched once
     launch_pdl(attn_prep_kernel, dim3(grid), dim3(kPrepThreads), (size_t)2 * ppb * pb.KQ * 2, st, p, pb.KQ, npix, pb.qa, pb.kb, pb.v);
     return 0;
 }
@@ -437,11 +437,7 @@ int launch_nt(const AttnParams &p, int L, cudaStream_t st) {
     if (MODE == MODE_ROW || MODE == MODE_COL) smem = std::max(smem, (size_t)(NT / 2) * kStageElems * 2);
     smem = (smem + 15) & ~size_t(15);
     if (smem * LPC > 227 * 1024) return 1;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(attn_mma_kernel<MODE, NT, LPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        attr_set = true;
-    }
+    if (RY_ENSURE_DYN_SMEM((attn_mma_kernel<MODE, NT, LPC>), 227 * 1024) != cudaSuccess) return 1;
     const int lines = (MODE == MODE_ROW) ? p.H : p.W;
     const int total = p.B * lines;
     const PrepBufs pb = prep_bufs(p);
@@ -475,7 +471,7 @@ void attn_qk_launch(const __nv_bfloat16 *x, int x_cs, int x_off, int C, int Cq, 
     (void)C;
     const size_t total = npix * Cq;
     size_t g = (total + 255) / 256;
-    if (g > (size_t)kNumSMs * 16) g = (size_t)kNumSMs * 16;
+    if (g > (size_t)num_sms() * 16) g = (size_t)num_sms() * 16;
     launch_pdl(attn_qk_kernel, dim3((int)g), dim3(256), 0, st, x, x_cs, x_off, Cq, npix, wq, bq, wk, bk, s, t, q, k);
 }
 

@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
 #include <string>
 
 namespace ry {
@@ -27,7 +28,23 @@ void set_error(const std::string &msg);   // plan.cu
         return 1;                           \
     } while (0)
 
-constexpr int kNumSMs = 148;
+// Multiprocessor count of the CURRENT device (cached per device; 148 on B200).  Grids of the persistent kernels are sized
+// from this, never from a compile-time constant.
+int num_sms();                              // plan.cu
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device function attribute: set it once per (kernel, device),
+// not once per process.  `kernel` may be a template instantiation (parenthesise it).  Evaluates to a cudaError_t.
+#define RY_ENSURE_DYN_SMEM(kernel, bytes)                                                                         \
+    ([&]() -> cudaError_t {                                                                                        \
+        static std::atomic<unsigned long long> done__{0ull};                                                       \
+        int dev__ = 0;                                                                                             \
+        cudaGetDevice(&dev__);                                                                                     \
+        const unsigned long long bit__ = 1ull << (dev__ & 63);                                                     \
+        if (done__.load(std::memory_order_acquire) & bit__) return cudaSuccess;                                    \
+        const cudaError_t e__ = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);  \
+        if (e__ == cudaSuccess) done__.fetch_or(bit__, std::memory_order_release);                                 \
+        return e__;                                                                                                \
+    }())
 
 // ---- programmatic dependent launch (PDL) ----
 // Every kernel of the forward pass is launched with the programmatic-stream-serialization attribute and

@@ -390,11 +390,7 @@ int chain_plan_smem(ChainArgs &a) {
 }
 
 void chain_launch(const ChainArgs &a, int grid, cudaStream_t stream) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(conv_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
-        attr_set = true;
-    }
+    RY_ENSURE_DYN_SMEM(conv_chain_kernel, kSmemLimit);
     launch_pdl(conv_chain_kernel, dim3(grid), dim3(kChainThreads), chain_smem_bytes(a), stream, a);
 }
 

@@ -384,6 +384,7 @@ __device__ __forceinline__ void epilogue_store_role(const ConvArgs &p, const Epi
 // two images or the end of the batch).  Two staging buffers: one 256-thread barrier per tile.
 // NO6 = true: the Rep-YOLO head (na = 3, no = 6) with every index computation on compile-time constants.
 constexpr int kDetHalf = 9;
+constexpr int kDetHalfMax = 16;      // generic heads: na*no <= 32 columns, ceil(nn / 2) per group
 template <bool NO6>
 __device__ __forceinline__ void epilogue_detect_role(const ConvArgs &p, const EpiCtx &cx) {
     const int e = cx.warp - 2, lane = cx.lane;
@@ -395,8 +396,10 @@ __device__ __forceinline__ void epilogue_detect_role(const ConvArgs &p, const Ep
     const int no = NO6 ? 6 : p.no, na = NO6 ? 3 : p.na, nn = na * no;
     const int rec = 128 * no;                                    // floats per anchor per tile
     const int tile_f = na * rec;                                 // floats per staged tile (one of decoded / raw)
-    const int col0 = grp * kDetHalf;
-    const int ldcol = grp ? kDetHalf - 1 : 0;                    // 16-column TMEM load window [ldcol, ldcol + 16) covers the group's columns
+    const int half = NO6 ? kDetHalf : (nn + 1) / 2;              // columns per group (generic head: any nn <= 32)
+    const int col0 = grp * half;
+    // NO6: one 16-column TMEM load window [ldcol, ldcol + 16) covers the group's 9 columns; generic: both 16-column halves
+    const int ldcol = NO6 ? (grp ? kDetHalf - 1 : 0) : 0;
     float *stage = reinterpret_cast<float *>(cx.sStage);
     const bool vec_ok = ((reinterpret_cast<uintptr_t>(p.pred) | reinterpret_cast<uintptr_t>(p.raw)) & 15) == 0 && (rec % 4) == 0 &&
                         ((p.img_hw * no) % 4) == 0 && (((size_t)p.rows_total * no) % 4) == 0 && (((size_t)p.row_off * no) % 4) == 0;
@@ -409,8 +412,9 @@ __device__ __forceinline__ void epilogue_detect_role(const ConvArgs &p, const Ep
         ptx::mbar_wait(cx.tfull + acc, aph);
         ptx::tc_fence_after();
         const uint32_t taddr = cx.tmem_base + acc * p.BN + ((uint32_t)(quarter * 32) << 16);
-        uint32_t raw[16];
+        uint32_t raw[NO6 ? 16 : 32];
         ptx::tmem_ld16_nowait(taddr + ldcol, raw);
+        if constexpr (!NO6) ptx::tmem_ld16_nowait(taddr + 16, raw + 16);      // generic head: all 32 columns
         ptx::tmem_ld_wait();
         ptx::tc_fence_before();
         __syncwarp();
@@ -421,11 +425,17 @@ __device__ __forceinline__ void epilogue_detect_role(const ConvArgs &p, const Ep
             const int rem = (int)(pix - (uint32_t)b * (uint32_t)p.img_hw);
             const int gy = (int)fast_div((uint32_t)rem, p.div_imgw), gx = rem - gy * p.img_w;
 #pragma unroll
-            for (int i = 0; i < kDetHalf; ++i) {
-                const int j = col0 + i;
-                if (j < nn) {
+            for (int i = 0; i < (NO6 ? kDetHalf : 2 * kDetHalfMax); ++i) {
+                // NO6: i walks the group's 9 columns, raw[j - ldcol]; generic: i walks all 32 accumulator columns (register
+                // indices stay compile-time), the group keeps its own [col0, col0 + half)
+                const int j = NO6 ? col0 + i : i;
+                const bool mine = NO6 ? (j < nn) : (j < nn && j >= col0 && j < col0 + half);
+                if (mine) {
                     const int a = j / no, o = j - a * no;
-                    const float tv = __uint_as_float(grp ? raw[i + 1] : raw[i]) + ld_shared_f(cx.sbias_u + (uint32_t)j * 4);   // raw[j - ldcol]
+                    uint32_t rv;
+                    if constexpr (NO6) rv = grp ? raw[i + 1] : raw[i];
+                    else rv = raw[i];
+                    const float tv = __uint_as_float(rv) + ld_shared_f(cx.sbias_u + (uint32_t)j * 4);
                     sr[a * rec + row * no + o] = tv;
                     sp[a * rec + row * no + o] = detect_decode(p, tv, a, o, gx, gy);
                 }
@@ -657,11 +667,7 @@ int conv_plan_smem(ConvArgs &a, int max_seg_cols) {
 }
 
 void conv_launch(const ConvArgs &a, int grid, cudaStream_t stream) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
-        attr_set = true;
-    }
+    RY_ENSURE_DYN_SMEM(conv_umma_kernel, kSmemLimit);
     launch_pdl(conv_umma_kernel, dim3(grid), dim3(64 + 128 * a.n_groups), conv_smem_bytes(a), stream, a);
 }
 

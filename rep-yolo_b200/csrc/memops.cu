@@ -726,7 +726,7 @@ __global__ void __launch_bounds__(256) ca_finish_kernel(const float *__restrict_
 
 inline int grid_for(size_t total, int block) {
     size_t g = (total + block - 1) / block;
-    const size_t cap = (size_t)kNumSMs * 16;
+    const size_t cap = (size_t)num_sms() * 16;
     return (int)(g < cap ? (g ? g : 1) : cap);
 }
 
@@ -737,12 +737,8 @@ void stem_launch_t(const void *img, const float *w27, const float *bias, __nv_bf
                    int W, cudaStream_t st) {
     const long tiles = (long)B * cdiv(H / 2, kStemTH) * cdiv(W / 2, kStemTW);
     const size_t smem = (size_t)2 * kStemPatchFloats * (U8 ? 1 : 4) + (size_t)2 * kStemTW * COUT * 2;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(stem_kernel<COUT, U8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-        attr_set = true;
-    }
-    const int grid = (int)std::min<long>(tiles, (long)kNumSMs * 2);
+    RY_ENSURE_DYN_SMEM((stem_kernel<COUT, U8>), 100 * 1024);
+    const int grid = (int)std::min<long>(tiles, (long)num_sms() * 2);
     launch_pdl(stem_kernel<COUT, U8>, dim3(grid), dim3(256), smem, st, img, w27, bias, out, B, H, W, out_cs, out_off);
 }
 
@@ -788,17 +784,14 @@ void dw5_launch(const __nv_bfloat16 *in, int in_cs, int in_off0, int in_off1, __
         m.stage_bytes = (m.halo_bytes + 208 * 16 + 127) & ~127;
         m.n_items = B * m.tiles_y * m.tiles_x * (C / 32);
         const int threads = 128 * m.swarps;
-        static bool attr_m = false;
-        if (!attr_m) {
-            cudaFuncSetAttribute(dw5_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            attr_m = true;
-        }
+        RY_ENSURE_DYN_SMEM(dw5_mma_kernel, 200 * 1024);
         launch_pdl(dw5_mma_kernel, dim3(m.n_items), dim3(threads), (size_t)m.stage_bytes + 16, st, m);   // + the TMA barrier
         return;
     }
     // tile = (4 SX) x (8 RG) pixels, SX * RG warps.  Model: an SM issues for ~16 warps at a time, so one round of n resident
     // CTAs costs n * warps; rounds = ceil(items / (148 n)); staged halo pixels per output pixel add L2 -> smem traffic.
     Dw5Args a = {};
+    const int n_sm = num_sms();
     double best = -1.0;
     for (int sx = 1; sx <= 16; ++sx)
         for (int rg = 1; rg * sx <= 16; ++rg) {
@@ -809,7 +802,7 @@ void dw5_launch(const __nv_bfloat16 *in, int in_cs, int in_off0, int in_off1, __
             if (2 * stage > 200 * 1024) continue;
             const int n_res = std::max(1, std::min((int)(220 * 1024 / (2 * stage)), 16 / warps));
             const long items = (long)B * cdiv(W, 4 * sx) * cdiv(H, 8 * rg) * (C / 32);
-            const double rounds = (double)((items + (long)kNumSMs * n_res - 1) / ((long)kNumSMs * n_res));
+            const double rounds = (double)((items + (long)n_sm * n_res - 1) / ((long)n_sm * n_res));
             const double halo = (double)(8 * rg + 4) * (4 * sx + 4) / (32.0 * warps);
             const double cost = rounds * n_res * warps * (1.0 + 0.08 * halo);
             if (best < 0 || cost < best) {
@@ -825,12 +818,8 @@ void dw5_launch(const __nv_bfloat16 *in, int in_cs, int in_off0, int in_off1, __
     a.C = C; a.half = half; a.H = H; a.W = W; a.act = act;
     const int warps = a.SX * a.RG;
     const int n_res = std::max(1, std::min((int)(220 * 1024 / (2 * (size_t)a.stage_bytes)), 16 / warps));
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(dw5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr_set = true;
-    }
-    launch_pdl(dw5_kernel, dim3(std::min(a.n_items, kNumSMs * n_res)), dim3(32 * warps), 2 * (size_t)a.stage_bytes, st, a);
+    RY_ENSURE_DYN_SMEM(dw5_kernel, 200 * 1024);
+    launch_pdl(dw5_kernel, dim3(std::min(a.n_items, n_sm * n_res)), dim3(32 * warps), 2 * (size_t)a.stage_bytes, st, a);
 }
 
 void maxpool2_launch(const __nv_bfloat16 *in, int in_cs, int in_off, __nv_bfloat16 *out, int out_cs, int out_off, int C,
@@ -845,11 +834,7 @@ void spp_launch(const __nv_bfloat16 *in, int in_cs, int in_off, __nv_bfloat16 *o
     int CH = ch0;
     while (CH > 8 && (C % CH != 0 || (size_t)2 * H * W * CH * 2 > 200 * 1024)) CH -= 8;
     const size_t smem = (size_t)2 * H * W * CH * 2;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(spp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        attr_set = true;
-    }
+    RY_ENSURE_DYN_SMEM(spp_kernel, 227 * 1024);
     launch_pdl(spp_kernel, dim3(B * (C / CH)), dim3(256), smem, st, in, in_cs, in_off, out, out_cs, off5, off9, off13, C, H, W, CH);
 }
 

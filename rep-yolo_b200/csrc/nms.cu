@@ -522,11 +522,7 @@ int nms_run(const float *pred, int B, int N, int nc, float conf, double iou, con
     }
     const size_t smem = (size_t)5 * kChunk * 4 + (size_t)kChunk * kChunkWords * 8 + (size_t)5 * ((max_det + 3) & ~3) * 4 + 2 * 4 +
                         (size_t)2 * kChunk * 4 + (kChunk / 32) * 4;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr_set = true;
-    }
+    RY_CUDA(RY_ENSURE_DYN_SMEM(nms_scan_kernel, 200 * 1024));
     IouThr thr;
     {   // smallest float strictly greater than the double threshold
         float tf = (float)iou;

@@ -26,6 +26,19 @@ namespace ry {
 static thread_local std::string g_error;
 void set_error(const std::string &msg) { g_error = msg; }
 
+int num_sms() {
+    static std::atomic<int> cache[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const int slot = dev & 63;
+    int n = cache[slot].load(std::memory_order_relaxed);
+    if (n <= 0) {
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cache[slot].store(n, std::memory_order_relaxed);
+    }
+    return n;
+}
+
 namespace {
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -413,7 +426,7 @@ int bind_conv(ry_plan *p, Op &op, std::vector<CUtensorMap> &maps) {
     a.cout = d.cout;
     a.act = d.act;
     const long tiles = (long)a.tiles_w * a.tiles_h * a.tiles_n * a.n_ntiles;
-    op.grid = (int)std::min<long>(tiles, kNumSMs);
+    op.grid = (int)std::min<long>(tiles, num_sms());
     op.launches = 1;
     if (d.kind == RY_OP_DETECT) {
         a.no = p->nc + 5;
@@ -576,7 +589,7 @@ int bind_chain(ry_plan *p, Op &op, std::vector<CUtensorMap> &maps) {
         maps.push_back(m);
     }
     const long tiles = (long)a.tiles_w * a.tiles_h * a.tiles_n;
-    op.grid = (int)std::min<long>(tiles, kNumSMs);
+    op.grid = (int)std::min<long>(tiles, num_sms());
     op.launches = 1;
     return 0;
 }
@@ -674,7 +687,6 @@ int run_op(ry_plan *p, Op &op, const float *image, float *pred, float *raws[3], 
             ap.out = bf(p, d.out0.tensor); ap.out_cs = to.d.channels; ap.out_off = d.out0.c_off;
             ap.scratch = reinterpret_cast<float *>(p->ws + p->scratch_off);
             const int rc = d.kind == RY_OP_CRISSCROSS ? crisscross_launch(ap, st) : vertical_launch(ap, st);
-            if (rc == 2) RY_FAIL("VerticalAttention with H != W is not built yet (reference view-chain semantics, SURVEY 8 a19)");
             if (rc) RY_FAIL("attention: unsupported shape (shared memory)");
             break;
         }

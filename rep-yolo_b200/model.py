@@ -133,6 +133,14 @@ class NativeEngine:
             self._image_u8 = u8
 
     def forward(self, x):
+        # the library reinterprets the buffer by element type: anything but contiguous fp32 / uint8 NCHW on this device
+        # would be read as garbage (and past its end), so it is an error here, never a silent cast
+        if x.dtype not in (torch.float32, torch.uint8):
+            raise N.NativeError(f'NativeEngine.forward: image dtype must be float32 or uint8, got {x.dtype}')
+        if x.dim() != 4 or x.shape[1] != 3 or not x.is_contiguous():
+            raise N.NativeError('NativeEngine.forward: image must be a contiguous [B, 3, H, W] tensor')
+        if x.device != self.device:
+            raise N.NativeError(f'NativeEngine.forward: image on {x.device}, engine on {self.device}')
         B, _, H, W = x.shape
         self.bind(B, H, W)
         self._set_image_dtype(x)
@@ -244,19 +252,35 @@ class Model(nn.Module):
             self._engines = {}
         return self
 
-    def forward(self, x, augment=False, profile=False):
-        if augment:
-            return self._forward_augment(x)
+    def _check_input(self, x):
+        """Shared by the plain and the augmented forward: deployed path only, CUDA only, fp32 (any other float type is
+        cast, e.g. the .half() image of test.py:104) or uint8 (detect.py:73; the /255 is fused in the stem)."""
         if self._fused is None:
             raise RuntimeError('only the deployed path is built: call .fuse() first (attempt_load does)')
+        if not torch.is_tensor(x) or x.dim() != 4:
+            raise ValueError('Model.forward: expected a [B, 3, H, W] tensor')
         if not x.is_cuda:
             raise N.NativeError('Model.forward: input must be a CUDA tensor (no CPU fallback on this path)')
         if x.dtype == torch.uint8:
-            x = x.contiguous()      # uint8 NCHW 0..255 (what detect.py:73 sends to the device): the /255 is fused in the stem
-        elif x.dtype != torch.float32 or not x.is_contiguous():
-            x = x.float().contiguous()
+            return x.contiguous()
+        if x.dtype != torch.float32 or not x.is_contiguous():
+            return x.float().contiguous()
+        return x
+
+    def forward(self, x, augment=False, profile=False):
+        x = self._check_input(x)
+        if augment:
+            return self._forward_augment(x)
         pred, raws = self.engine(x.device, (x.shape[0], x.shape[2], x.shape[3])).forward(x)
         return self.model[-1]._package(pred, raws)
+
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        """New weights invalidate the folded copy and every bound engine (they hold packed bf16 weights): .fuse() again."""
+        out = super().load_state_dict(state_dict, strict=strict, **kw)
+        self._fused = None
+        self._engine = None
+        self._engines = {}
+        return out
 
     def _forward_augment(self, x):
         """Test-time augmentation exactly as the reference (models/yolo.py:570-585, utils/torch_utils.py:247-257): scales
@@ -277,7 +301,7 @@ class Model(nn.Module):
                 xi = F.interpolate(xi, size=s, mode='bilinear', align_corners=False)
                 h, w = [math.ceil(v * si / gs) * gs for v in (h, w)]
                 xi = F.pad(xi, [0, w - s[1], 0, h - s[0]], value=0.447)
-            yi = self.engine(xi.device, (xi.shape[0], xi.shape[2], xi.shape[3])).forward(xi.contiguous())[0]
+            yi = self.engine(xi.device, (xi.shape[0], xi.shape[2], xi.shape[3])).forward(xi.float().contiguous())[0]
             yi[..., :4] /= si
             if fi == 3:
                 yi[..., 0] = img_size[1] - yi[..., 0]

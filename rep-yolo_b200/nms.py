@@ -41,6 +41,8 @@ def nms_padded(prediction, conf_thres=0.25, iou_thres=0.45, classes=None, agnost
     counts = torch.zeros((B,), dtype=torch.int32, device=p.device)
     if B == 0 or n == 0:
         return out, counts
+    if classes is not None and len(classes) == 0:
+        return out, counts          # general.py:1012-1013: an empty class list matches no row (None = no filter)
     ws = _workspace(p.device, B, n, nc, multi_label)
     cls = np.ascontiguousarray(np.asarray(classes if classes is not None else [], dtype=np.int32).reshape(-1))
     with torch.cuda.device(p.device):

@@ -254,3 +254,68 @@ def test_idetect_output_contracts():
     out = m(x)
     assert isinstance(out, list) and len(out) == 3 and torch.equal(out[0], raws[0])
     det.export = False
+
+
+def test_tta_augment_half_input_is_cast_not_reinterpreted():
+    """test.py:104 sends img.half(); the augmented path must normalise the dtype like the plain forward."""
+    import repyolo_b200 as R
+    layers, save, sd, fz = O.make_model(seed=0, mode='default')
+    m = R.Model()
+    m.load_state_dict(sd, strict=True)
+    m.fuse()
+    x = torch.rand(1, 3, 128, 128, generator=torch.Generator().manual_seed(12)).cuda()
+    ref, _ = m(x.half().float(), augment=True)
+    got, _ = m(x.half(), augment=True)
+    assert torch.equal(got, ref)
+    with pytest.raises(R.NativeError):
+        m.engine(x.device).forward(x.half())          # the engine itself never reinterprets a foreign dtype
+    with pytest.raises(R.NativeError):
+        m.engine(x.device).forward(x.permute(0, 1, 3, 2))
+
+
+def test_load_state_dict_after_fuse_invalidates():
+    import repyolo_b200 as R
+    layers, save, sd, fz = O.make_model(seed=0, mode='default')
+    m = R.Model()
+    m.load_state_dict(sd, strict=True)
+    m.fuse()
+    x = torch.rand(1, 3, 64, 64).cuda()
+    m(x)
+    m.load_state_dict(sd, strict=True)
+    with pytest.raises(RuntimeError):
+        m(x)
+    m.fuse()
+    m(x)
+
+
+def test_detect_decode_nc2_generic_head():
+    """Detect epilogue with na*(nc+5) = 21 columns (nc = 2): the generic column split (columns >= 18 used to be
+    left unstaged).  Teacher-forced from normalised random features, same-operand check + stated decode tolerance."""
+    import torch.nn.functional as F
+    import repyolo_b200 as R
+    from gpu_util import nchw_to_arena
+    layers, save, sd, fz = O.make_model(seed=0, mode='calibrated', nc=2)
+    m = R.Model(nc=2)
+    m.load_state_dict(sd, strict=True)
+    m.fuse()
+    B, H, W = 2, 96, 160
+    eng = m.engine('cuda:0')
+    eng.bind(B, H, W)
+    g = eng.plan_ir.groups[-1]
+    gen = torch.Generator().manual_seed(21)
+    feats = [torch.randn(B, c, H >> l, W >> l, generator=gen) for c, l in ((256, 3), (512, 4), (1024, 5))]
+    for (src, view), f in zip(g.inputs, feats):
+        nchw_to_arena(eng, view, f)
+    pred, raws = eng._outputs(B, H, W)
+    assert pred.shape[-1] == 7
+    eng.run_ops(g.first_op, g.last_op, pred=pred, raws=raws)
+    torch.cuda.synchronize()
+    ag = fz['model.65.anchor_grid']
+    heads_b = [F.conv2d(f.bfloat16().float(), fz[f'model.65.m.{j}.weight'].bfloat16().float(), fz[f'model.65.m.{j}.bias'])
+               for j, f in enumerate(feats)]
+    pred_b, raws_b = O.decode_heads(heads_b, ag)
+    for a, b in zip(raws, raws_b):
+        assert a.shape == b.shape
+        assert bool(((a.cpu() - b).abs() <= 2e-4 * (1 + b.abs())).all()), float((a.cpu() - b).abs().max())
+    p = pred.cpu()
+    assert bool(((p - pred_b).abs() <= 2e-3 + 1e-4 * pred_b.abs()).all()), float((p - pred_b).abs().max())

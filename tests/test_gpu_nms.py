@@ -102,3 +102,12 @@ def test_full_size_properties():
     rows = torch.stack([(d[:, 0] + d[:, 2]) / 2, (d[:, 1] + d[:, 3]) / 2, d[:, 2] - d[:, 0], d[:, 3] - d[:, 1], d[:, 4], d[:, 4]], 1)
     again = R.non_max_suppression(rows[None].contiguous(), 0.001, 0.65)
     assert again[0].shape[0] >= d.shape[0] - 2                          # re-derived xyxy can move by an ulp
+
+
+def test_empty_class_list_matches_nothing():
+    """general.py:1012-1013: classes=[] keeps no row (classes=None means no filter)."""
+    import repyolo_b200 as R
+    pred = torch.rand(2, 500, 6, generator=torch.Generator().manual_seed(1)).cuda()
+    pred[..., :4] *= 300
+    assert all(d.shape == (0, 6) for d in R.non_max_suppression(pred, 0.25, 0.45, classes=[]))
+    assert any(d.shape[0] > 0 for d in R.non_max_suppression(pred, 0.25, 0.45, classes=None))

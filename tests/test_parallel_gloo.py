@@ -23,6 +23,13 @@ def _worker(rank, world, port, ret):
     ok = torch.equal(out, full_out) and torch.equal(cnt, full_cnt)
     lst = R.to_list(out, cnt)
     ok = ok and all(l.shape[0] == int(c) for l, c in zip(lst, full_cnt))
+    # uneven shards (7 images over 2 ranks: 4 + 3): padded for the collective, padding dropped afterwards
+    n7 = 7
+    f_out = torch.rand(n7, max_det, 6, generator=g)
+    f_cnt = torch.randint(0, max_det + 1, (n7,), generator=g, dtype=torch.int32)
+    lo, hi = R.shard_bounds(n7, rank, world)
+    out7, cnt7 = R.gather_detections(f_out[lo:hi].clone(), f_cnt[lo:hi].clone(), n_images=n7)
+    ok = ok and torch.equal(out7, f_out) and torch.equal(cnt7, f_cnt)
     ret[rank] = bool(ok)
     dist.destroy_process_group()
 
