@@ -98,6 +98,41 @@ class ClockSampler(threading.Thread):
         return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': self.max_mhz, 'reasons': reasons, 'samples': len(sm)}
 
 
+def host_cores():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+def pin_to_gpu_numa(local_rank):
+    """Bind this rank (and the pinned host buffers it allocates afterwards: first touch) to the NUMA node of its GPU.
+    Returns a short description for the JSON line.  Best effort: silently a no-op when sysfs / NVML do not tell."""
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        vis = [v for v in os.environ.get('CUDA_VISIBLE_DEVICES', '').split(',') if v.strip().isdigit()]
+        idx = int(vis[local_rank]) if local_rank < len(vis) else local_rank
+        bus = nv.nvmlDeviceGetPciInfo(nv.nvmlDeviceGetHandleByIndex(idx)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(':')[0]) == 8:
+            bus = bus[4:]
+        node = int(open(f'/sys/bus/pci/devices/{bus}/numa_node').read().strip())
+        if node < 0:
+            return 'numa node unknown (-1)'
+        cpus = set()
+        for part in open(f'/sys/devices/system/node/node{node}/cpulist').read().strip().split(','):
+            lo, _, hi = part.partition('-')
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f'rank pinned to NUMA node {node} ({len(cpus)} cpus)'
+        return f'NUMA node {node}: no allowed cpus, not pinned'
+    except Exception as e:                      # noqa: BLE001
+        return f'not pinned ({type(e).__name__})'
+
+
 def oracle_step(fz, layers, save, x, torch, O, nms_oracle):
     """the reference's CPU path (oracle port): fused forward + non_max_suppression"""
     _, pred, _ = O.forward_fused(fz, layers, save, x)
@@ -109,6 +144,9 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
+    # rank 0 alone runs the CPU arm, so it takes every host core this process may use; torch.distributed.run exports
+    # OMP_NUM_THREADS=1, which would otherwise cripple the reference at N > 1 (round-1 verdict)
+    torch.set_num_threads(host_cores())
     from oracle import nms_oracle
     from oracle import repyolo_oracle as O
     nms_oracle.build()
@@ -144,15 +182,40 @@ def workload_config(args):
             'parallelism': f'batch-sharded dp{args.gpus}, NCCL all-gather of [B,300,6] detections' if args.gpus > 1 else 'single GPU'}
 
 
+def memory_class_bytes(d, tensors, B, S):
+    """Algorithmic HBM bytes of one memory-bound op (bf16 NHWC, read once + write once) and its class name."""
+    lvl = tensors[d.in0.tensor].level
+    h = w = S >> lvl
+    px = float(B * h * w)
+    if d.kind == 1:      # stem: fp32 (or uint8) NCHW image in, 48-channel bf16 map at half resolution out
+        return 'stem', B * 3.0 * S * S * 4 + B * (S // 2) * (S // 2) * d.cout * 2.0
+    if d.kind == 3:      # depthwise 5x5: in + out
+        return 'dw5', 2.0 * px * d.cin * 2
+    if d.kind == 4:
+        return 'maxpool2', px * d.cin * 2 * 1.25
+    if d.kind == 5:      # one read, three writes
+        return 'spp', px * d.cin * 2 * 4.0
+    if d.kind == 6:
+        return 'upsample2', px * d.cin * 2 * 5.0
+    if d.kind == 7:
+        return 'ca', px * d.cin * 2
+    if d.kind in (9, 10):    # x in, gamma*out + x out
+        return 'attention', 2.0 * px * d.cin * 2
+    if d.kind == 11:     # head input + decoded pred + raw head tensor (fp32)
+        return 'detect', px * d.cin * 2 + 2.0 * px * d.cout * 4
+    return None, 0.0
+
+
 def run_native(args):
     import torch
     import torch.distributed as dist
-    import repyolo_b200 as R
-    from oracle import repyolo_oracle as O          # weights generator + the cpu_baseline leg only
-
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
+    numa = pin_to_gpu_numa(local) if world > 1 else 'single rank: not pinned'
+    import repyolo_b200 as R
+    from oracle import repyolo_oracle as O          # weights generator + the cpu_baseline leg only
+
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device(f'cuda:{local}'))
     assert world == args.gpus, f'--gpus {args.gpus} but WORLD_SIZE={world} (launch N>1 with torch.distributed.run)'
@@ -174,14 +237,24 @@ def run_native(args):
     xdev = [h.to(dev) for h in host]
     eng = model.engine(dev)
     eng.bind(B, S, S)
-    launches_per_step = eng.launch_count() + 3    # + NMS: filter, one-kernel sort (cap <= 32768 candidates per image), scan
+    launches_per_step = eng.launch_count() + R.nms_launch_count(B, eng.n_cand, 1)
+    gat = R.DetectionGatherer(B, 300, dev) if world > 1 else None
 
-    def step(x):
+    def step(x, i=0):
+        """one pass of the hot path: forward (convs + decode) + NMS; N > 1: the detections go out on the side stream"""
         pred, _ = model(x)
-        out, counts = R.nms_padded(pred, CONF, IOU)
-        if world > 1:
-            out, counts = R.gather_detections(out, counts)
+        if gat is None:
+            return R.nms_padded(pred, CONF, IOU)
+        out, counts = gat.slot(i)
+        R.nms_padded(pred, CONF, IOU, out=out, counts=counts)
+        gat.launch(i)
         return out, counts
+
+    def drain(n):
+        """the timed region ends when the last gathers have landed"""
+        if gat is not None:
+            for i in range(max(0, n - gat.nb), n):
+                gat.result(i)
 
     def sync_all():
         torch.cuda.synchronize(dev)
@@ -193,20 +266,34 @@ def run_native(args):
     sampler = ClockSampler(local, str(getattr(torch.cuda.get_device_properties(dev), 'uuid', '') or ''))
     sampler.start()
     for i in range(args.warmup):
-        step(xdev[i % n_bufs])
+        step(xdev[i % n_bufs], i)
+    drain(args.warmup)
     sync_all()
     sampler.wait_first()
     for i in range(args.warmup):                      # GPU busy again right before the timed region (the wait above idled it)
-        step(xdev[i % n_bufs])
+        step(xdev[i % n_bufs], i)
+    drain(args.warmup)
     sync_all()
     mark = sampler.mark()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
-        out, counts = step(xdev[i % n_bufs])
+        out, counts = step(xdev[i % n_bufs], i)
+    drain(args.steps)
     e1.record()
     sync_all()
     ms = e0.elapsed_time(e1)
+
+    # ---- N > 1: the gathered block of this rank equals what it computed locally (NCCL order check) ----
+    gather_ok = None
+    if gat is not None:
+        last = args.steps - 1
+        go, gc = gat.result(last)
+        lo, lc = gat.slot(last)                       # same buffer the last step wrote (nothing was launched since)
+        ok = torch.equal(go[rank], lo) and torch.equal(gc[rank], lc) and int(gc.min()) >= 0 and int(gc.max()) <= 300
+        okt = torch.tensor([1 if ok else 0], device=dev)
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+        gather_ok = bool(int(okt.item()))
 
     # ---- end to end through the public API: pinned host batch -> H2D -> forward -> NMS -> D2H of the detections ----
     copy_stream = torch.cuda.Stream(dev)
@@ -214,8 +301,9 @@ def run_native(args):
     staged = [torch.empty((B, 3, S, S), dtype=torch.uint8, device=dev) for _ in range(2)]
     ready = [torch.cuda.Event() for _ in range(2)]
     freed = [torch.cuda.Event() for _ in range(2)]
-    res_out = torch.empty((B * world, 300, 6), dtype=torch.float32).pin_memory()
-    res_cnt = torch.empty((B * world,), dtype=torch.int32).pin_memory()
+    d2h_floats = (gat.plen * world) if gat is not None else B * 300 * 6
+    res_out = torch.empty((d2h_floats,), dtype=torch.float32).pin_memory()
+    res_cnt = torch.empty((B,), dtype=torch.int32).pin_memory()
 
     def e2e_loop(n):
         for j in range(2):
@@ -232,11 +320,20 @@ def run_native(args):
                     staged[nxt].copy_(host8[(i + 1) % n_bufs], non_blocking=True)
                     ready[nxt].record(copy_stream)
             main.wait_event(ready[cur])
-            o, c = step(staged[cur])
+            o, c = step(staged[cur], i)
             freed[cur].record(main)
-            res_out.copy_(o, non_blocking=True)
-            res_cnt.copy_(c, non_blocking=True)
+            if gat is None:
+                res_out.copy_(o.view(-1), non_blocking=True)
+                res_cnt.copy_(c, non_blocking=True)
+            else:                                     # the gathered payload (rows + counts of all ranks) comes back on the side stream
+                with torch.cuda.stream(gat.side):
+                    gat.result(i, gat.side)
+                    res_out.copy_(gat.recv[i % gat.nb], non_blocking=True)
+                    gat.done[i % gat.nb].record(gat.side)
+        drain(n)
         main.synchronize()
+        if gat is not None:
+            gat.side.synchronize()
 
     e2e_loop(max(2, args.warmup))
     sync_all()
@@ -248,7 +345,58 @@ def run_native(args):
     ms_e2e = t0.elapsed_time(t1)
     clocks = sampler.stop(mark)                        # samples taken from the start of the first timed region to the end of the second
 
-    # ---- roofline of the dominant kernel (conv_umma_kernel): per-op CUDA events over K more steps ----
+    # ---- the drop-in list API (non_max_suppression -> list of (n, 6) tensors: one D2H read of the counts per call) ----
+    def list_api_loop(n):
+        for i in range(n):
+            pred, _ = model(xdev[i % n_bufs])
+            dets = R.non_max_suppression(pred, CONF, IOU)
+        return dets
+    list_api_loop(2)
+    torch.cuda.synchronize(dev)
+    n_list = min(args.steps, 10)
+    tl = time.perf_counter()
+    list_api_loop(n_list)
+    torch.cuda.synchronize(dev)
+    ms_list = 1e3 * (time.perf_counter() - tl) / n_list
+
+    # ---- NMS legs: the bench weights, and BASELINE's seeded default init (all 25200 candidates pass, decided by tie-break) ----
+    def nms_leg(pred):
+        R.nms_padded(pred, CONF, IOU)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 10
+        a.record()
+        for _ in range(reps):
+            o, c = R.nms_padded(pred, CONF, IOU)
+        b.record()
+        torch.cuda.synchronize(dev)
+        t = a.elapsed_time(b) / reps
+        by = pred.numel() * 4.0 + o.numel() * 4.0
+        return {'ms_per_step': t, 'candidates_per_image': float((pred[..., 4] > CONF).sum().item()) / pred.shape[0],
+                'detections_per_image': float(c.float().mean().item()), 'algorithmic_gbytes_per_s': by / (t * 1e-3) / 1e9,
+                'frac_of_hbm_peak': by / (t * 1e-3) / 1e9 / peaks()['hbm']}
+    pred_main, _ = model(xdev[0])
+    nms_legs = {args.init: nms_leg(pred_main)}
+    other = 'default' if args.init != 'default' else 'calibrated'
+    if rank == 0 and not args.no_nms_legs:
+        _, _, sd2, _ = O.make_model(seed=0, mode=other)
+        m2 = R.Model()
+        m2.load_state_dict(sd2, strict=True)
+        m2.fuse()
+        pred2, _ = m2(xdev[0])
+        nms_legs[other + '_init'] = nms_leg(pred2)
+        e0b, e1b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(3):
+            R.nms_padded(m2(xdev[0])[0], CONF, IOU)
+        e0b.record()
+        for i in range(10):
+            R.nms_padded(m2(xdev[i % n_bufs])[0], CONF, IOU)
+        e1b.record()
+        torch.cuda.synchronize(dev)
+        nms_legs[other + '_init']['whole_step_images_per_s_1gpu'] = B * 10 / (e0b.elapsed_time(e1b) * 1e-3)
+        del m2, pred2
+    nms_legs[args.init + '_init'] = nms_legs.pop(args.init)
+
+    # ---- roofline: per-op CUDA events over K more steps (conv family vs bf16 peak, memory-bound classes vs HBM peak) ----
     ops = eng.plan_ir.ops
     eng.set_profiling(True)
     conv_ms, all_ms, per_op = 0.0, 0.0, [0.0] * len(ops)
@@ -263,8 +411,13 @@ def run_native(args):
     pk = peaks()
     ridge = pk['tf_sustained'] * 1e12 / (pk['hbm'] * 1e9)          # FLOP per HBM byte at which a conv turns tensor-bound
     cls = {'tensor': [0.0, 0.0, 0.0, 0], 'hbm': [0.0, 0.0, 0.0, 0]}  # [flops, bytes, ms, launches]
+    mem = {}                                                           # memory-bound classes: [bytes, ms, ops]
     for j, d in enumerate(ops):
         all_ms += per_op[j]
+        name, mby = memory_class_bytes(d, eng.plan_ir.tensors, B, S)
+        if name:
+            m = mem.setdefault(name, [0.0, 0.0, 0])
+            m[0] += mby; m[1] += per_op[j]; m[2] += 1
         if d.kind in (2, 11, 12):    # RY_OP_CONV, RY_OP_DETECT (conv_umma_kernel), RY_OP_CONV_CHAIN (conv_chain_kernel)
             conv_ms += per_op[j]
             lvl = eng.plan_ir.tensors[d.in0.tensor].level
@@ -292,6 +445,15 @@ def run_native(args):
             detail[name + '_bound_layers'] = {
                 'launches': n, 'ms_per_step': t, 'tflops': fl / (t * 1e-3) / 1e12, 'frac_of_bf16_peak': fl / (t * 1e-3) / 1e12 / pk['tf_sustained'],
                 'algorithmic_gbytes_per_s': by / (t * 1e-3) / 1e9, 'frac_of_hbm_peak': by / (t * 1e-3) / 1e9 / pk['hbm']}
+    hbm_classes = {}
+    for name, (by, t, n) in sorted(mem.items()):
+        t /= prof_steps
+        if t > 0:
+            hbm_classes[name] = {'ops': n, 'ms_per_step': t, 'algorithmic_mbytes_per_step': by / 1e6,
+                                 'algorithmic_gbytes_per_s': by / (t * 1e-3) / 1e9, 'frac_of_hbm_peak': by / (t * 1e-3) / 1e9 / pk['hbm']}
+    leg = nms_legs[args.init + '_init']
+    hbm_classes['nms'] = {'ops': 1, 'ms_per_step': leg['ms_per_step'], 'algorithmic_mbytes_per_step': (pred_main.numel() + B * 1800) * 4 / 1e6,
+                          'algorithmic_gbytes_per_s': leg['algorithmic_gbytes_per_s'], 'frac_of_hbm_peak': leg['frac_of_hbm_peak']}
     traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, 'profiles', 'conv_traffic.json')
     if os.path.exists(tpath):           # dram__bytes_read+write per conv launch from the committed ncu capture of this workload
@@ -307,13 +469,18 @@ def run_native(args):
     e2e_v = B * world * args.steps / (ms_e2e * 1e-3)
 
     if rank == 0:
+        cfg = workload_config(args)
+        cfg['numa'] = numa
         line = {'metric': METRIC, 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
                 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16',
-                'data': 'synthetic', 'config': workload_config(args), 'clocks': clocks,
+                'data': 'synthetic', 'config': cfg, 'clocks': clocks,
                 'e2e': {'value': e2e_v, 'unit': 'images/s', 'h2d_bytes_per_step': B * 3 * S * S,
                         'input': 'uint8 NCHW from pinned host memory, /255 fused in the stem kernel (reference: detect.py:73-78)',
-                        'd2h_bytes_per_step': B * world * (300 * 6 * 4 + 4), 'ms_per_step': ms_e2e / args.steps,
-                        'pipeline': 'H2D of batch i+1 overlaps compute of batch i (2 pinned buffers, copy stream)'},
+                        'd2h_bytes_per_step': d2h_floats * 4 + (B * 4 if gat is None else 0), 'ms_per_step': ms_e2e / args.steps,
+                        'pipeline': 'H2D of batch i+1 overlaps compute of batch i (2 pinned buffers, copy stream)' +
+                                    ('; detections of batch i are gathered (one fused rows+counts payload) and read back on a side stream while batch i+1 computes' if gat is not None else ''),
+                        'list_api': {'images_per_s_per_gpu': B / (ms_list * 1e-3), 'ms_per_step': ms_list,
+                                     'what': 'Model.forward + non_max_suppression() -> list of (n,6) tensors (the reference signature; one host read of the counts per call), device-resident input, wall clock'}},
                 'gpu_launches': launches_per_step * args.steps,
                 'roofline': {'bound': 'tensor', 'kernel': 'conv_umma_kernel (+ conv_chain_kernel: fused 3x3->1x1 chains of the same design)', 'achieved': achieved, 'peak': pk['tf_sustained'],
                              'unit': 'TFLOP/s', 'frac': achieved / pk['tf_sustained'], 'traffic': traffic, 'traffic_source': traffic_src,
@@ -322,11 +489,16 @@ def run_native(args):
                              'conv_ms_per_step': conv_ms, 'all_ops_ms_per_step': all_ms,
                              'algorithmic_gflop_per_image': conv_flops / B / 1e9,
                              'algorithmic_bytes_per_launch': sum(c[1] for c in cls.values()) / max(n_conv, 1),
-                             'ridge_flop_per_byte': ridge, 'detail': detail},
+                             'ridge_flop_per_byte': ridge, 'detail': detail,
+                             'hbm_classes': hbm_classes, 'hbm_peak_gbytes_per_s': pk['hbm']},
+                'nms': nms_legs,
                 'cpu_baseline': None}
+        if gather_ok is not None:
+            line['gather_ok'] = gather_ok
         if world == 1 and not args.no_cpu_baseline:
             from oracle import nms_oracle
             nms_oracle.build()
+            torch.set_num_threads(host_cores())
             n = max(1, min(args.ref_sample, B))
             xs = host[0][:n].clone()
             oracle_step(fz, layers, save, xs[:1], torch, O, nms_oracle)
@@ -341,6 +513,7 @@ def run_native(args):
                                     'host_cpus': os.cpu_count()}
         print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -352,9 +525,12 @@ def main():
     ap.add_argument('--impl', default='native', choices=['native', 'reference'])
     ap.add_argument('--batch', type=int, default=64)
     ap.add_argument('--size', type=int, default=640)
-    ap.add_argument('--init', default='calibrated', choices=['calibrated', 'default'])
+    ap.add_argument('--init', default='default', choices=['calibrated', 'default'],
+                    help="'default' = the seeded default random init BASELINE.json configs[0-1] name (all 25200 candidates pass the conf filter); "
+                         "'calibrated' = SURVEY App. D statistics-calibrated init (realistic candidate counts)")
     ap.add_argument('--ref-sample', type=int, default=4, help='images per step of the CPU reference arm / cpu_baseline')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-nms-legs', action='store_true', help='skip the second-init NMS leg (A/B runs)')
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == 'native':
         args.warmup = 3

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define RY_ABI_VERSION 3
+#define RY_ABI_VERSION 4
 
 typedef struct ry_plan ry_plan;
 
@@ -150,6 +150,7 @@ int ry_plan_op_times(ry_plan *plan, float *ms_host, int n);
 /* non_max_suppression.  pred: fp32 [B,N,5+nc] (not modified).  out: fp32 [B,max_det,6] rows (x1,y1,x2,y2,conf,cls)
  * in score order, counts: int32 [B].  classes: HOST array or NULL.  iou_thres is compared in double like torchvision. */
 int ry_nms_workspace_bytes(int B, int N, int nc, int multi_label, size_t *bytes);
+int ry_nms_launch_count(int B, int N, int nc, int multi_label, int *n);   /* kernels one ry_nms call launches (bench.py's gpu_launches) */
 int ry_nms(const float *pred, int B, int N, int nc, float conf_thres, double iou_thres, const int32_t *classes_host,
            int n_classes, int agnostic, int multi_label, int max_det, int max_nms, float *out, int32_t *counts,
            void *workspace, size_t workspace_bytes, void *stream);

@@ -976,6 +976,12 @@ int ry_nms_workspace_bytes(int B, int N, int nc, int multi_label, size_t *bytes)
     return 0;
 }
 
+int ry_nms_launch_count(int B, int N, int nc, int multi_label, int *n) {
+    if (!n || B <= 0 || N <= 0 || nc <= 0) RY_FAIL("nms_launch_count: bad arguments");
+    *n = nms_launch_count(B, N, nc, multi_label);
+    return 0;
+}
+
 int ry_nms(const float *pred, int B, int N, int nc, float conf_thres, double iou_thres, const int32_t *classes_host,
            int n_classes, int agnostic, int multi_label, int max_det, int max_nms, float *out, int32_t *counts, void *workspace,
            size_t workspace_bytes, void *stream) {

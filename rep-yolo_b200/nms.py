@@ -26,9 +26,17 @@ def _workspace(device, B, n, nc, multi_label):
     return ws
 
 
+def nms_launch_count(B, n, nc, multi_label=False):
+    """kernel launches of one nms_padded / non_max_suppression call (bench.py's gpu_launches claim)"""
+    k = C.c_int()
+    N.check(N.lib().ry_nms_launch_count(B, n, nc, int(bool(multi_label) and nc > 1), C.byref(k)), 'ry_nms_launch_count')
+    return k.value
+
+
 def nms_padded(prediction, conf_thres=0.25, iou_thres=0.45, classes=None, agnostic=False, multi_label=False,
-               max_det=MAX_DET, max_nms=MAX_NMS):
-    """Device-side result without any host sync: (out [B, max_det, 6] fp32, counts [B] int32)."""
+               max_det=MAX_DET, max_nms=MAX_NMS, out=None, counts=None):
+    """Device-side result without any host sync: (out [B, max_det, 6] fp32, counts [B] int32).
+    ``out`` / ``counts``: optional preallocated contiguous destinations (e.g. views of a gather payload)."""
     if not prediction.is_cuda:
         raise N.NativeError('non_max_suppression: prediction must be a CUDA tensor (no CPU fallback on this path)')
     p = prediction.detach()
@@ -37,11 +45,17 @@ def nms_padded(prediction, conf_thres=0.25, iou_thres=0.45, classes=None, agnost
     B, n, no = p.shape
     nc = no - 5
     multi_label = bool(multi_label) and nc > 1
-    out = torch.empty((B, max_det, 6), dtype=torch.float32, device=p.device)
-    counts = torch.zeros((B,), dtype=torch.int32, device=p.device)
+    if out is None:
+        out = torch.empty((B, max_det, 6), dtype=torch.float32, device=p.device)
+    if counts is None:
+        counts = torch.zeros((B,), dtype=torch.int32, device=p.device)
+    if (tuple(out.shape) != (B, max_det, 6) or out.dtype != torch.float32 or not out.is_contiguous() or out.device != p.device or
+            tuple(counts.shape) != (B,) or counts.dtype != torch.int32 or not counts.is_contiguous() or counts.device != p.device):
+        raise ValueError('nms_padded: out must be contiguous fp32 [B, max_det, 6] and counts int32 [B] on the prediction device')
     if B == 0 or n == 0:
         return out, counts
     if classes is not None and len(classes) == 0:
+        counts.zero_()
         return out, counts          # general.py:1012-1013: an empty class list matches no row (None = no filter)
     ws = _workspace(p.device, B, n, nc, multi_label)
     cls = np.ascontiguousarray(np.asarray(classes if classes is not None else [], dtype=np.int32).reshape(-1))

@@ -43,6 +43,65 @@ def gather_detections(out: torch.Tensor, counts: torch.Tensor, group=None, n_ima
     return g_out, g_cnt
 
 
+class DetectionGatherer:
+    """Asynchronous detection gather ("overlap with the next batch on a side stream").
+
+    One fused payload per rank and step -- the [B_local, max_det, 6] fp32 rows with the [B_local] int32 counts packed
+    behind them -- goes out as ONE all_gather on a side stream, double buffered, so the compute stream never waits for the
+    slowest rank: step i+1's forward runs while step i's detections travel.  ``slot(i)`` hands out the (out, counts) views
+    ry_nms writes into (no staging copy), ``launch(i)`` starts the collective once the compute stream has produced them,
+    ``result(i)`` makes the CURRENT stream wait for it and returns ([world, B_local, max_det, 6], [world, B_local]) views
+    of the gathered payload (global image order = rank-major)."""
+
+    def __init__(self, b_local: int, max_det: int, device, group=None, n_buffers: int = 2):
+        self.group, self.device = group, torch.device(device)
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.b, self.max_det, self.nb = b_local, max_det, n_buffers
+        self.rows = b_local * max_det * 6
+        self.plen = self.rows + ((b_local + 3) // 4) * 4            # floats per rank payload (counts as int32 bit patterns)
+        self.send = [torch.zeros(self.plen, dtype=torch.float32, device=self.device) for _ in range(n_buffers)]
+        self.recv = [torch.zeros(self.world * self.plen, dtype=torch.float32, device=self.device) for _ in range(n_buffers)]
+        on_gpu = self.device.type == 'cuda'
+        self.side = torch.cuda.Stream(self.device) if on_gpu else None
+        self.produced = [torch.cuda.Event() for _ in range(n_buffers)] if on_gpu else None
+        self.done = [torch.cuda.Event() for _ in range(n_buffers)] if on_gpu else None
+        self.pending = [False] * n_buffers
+
+    def slot(self, i: int):
+        """(out [B_local, max_det, 6] fp32, counts [B_local] int32) views of send buffer i % n_buffers.  The compute stream
+        first waits until the collective that last read this buffer has finished."""
+        k = i % self.nb
+        if self.side is not None and self.pending[k]:
+            torch.cuda.current_stream(self.device).wait_event(self.done[k])
+        buf = self.send[k]
+        return buf[:self.rows].view(self.b, self.max_det, 6), buf[self.rows:self.rows + self.b].view(torch.int32)
+
+    def launch(self, i: int):
+        k = i % self.nb
+        if self.world == 1:
+            self.recv[k].copy_(self.send[k], non_blocking=True)
+            return
+        if self.side is None:                                       # CPU tensors (gloo): synchronous
+            dist.all_gather_into_tensor(self.recv[k], self.send[k], group=self.group)
+            return
+        self.produced[k].record(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(self.produced[k])
+            dist.all_gather_into_tensor(self.recv[k], self.send[k], group=self.group)
+            self.done[k].record(self.side)
+        self.pending[k] = True
+
+    def views(self, i: int):
+        g = self.recv[i % self.nb].view(self.world, self.plen)
+        return (g[:, :self.rows].view(self.world, self.b, self.max_det, 6), g[:, self.rows:self.rows + self.b].view(torch.int32))
+
+    def result(self, i: int, stream=None):
+        k = i % self.nb
+        if self.side is not None and self.pending[k]:
+            (stream or torch.cuda.current_stream(self.device)).wait_event(self.done[k])
+        return self.views(i)
+
+
 def to_list(out: torch.Tensor, counts: torch.Tensor):
     """padded -> the reference's list of (n_i, 6) tensors (one host read of the counts)."""
     return [out[i, :c] for i, c in enumerate(counts.cpu().tolist())]

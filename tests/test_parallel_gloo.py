@@ -19,6 +19,7 @@ def _worker(rank, world, port, ret):
     full_out = torch.rand(n_images, max_det, 6, generator=g)
     full_cnt = torch.randint(0, max_det + 1, (n_images,), generator=g, dtype=torch.int32)
     lo, hi = R.shard_bounds(n_images, rank, world)
+    lo0, hi0 = lo, hi
     out, cnt = R.gather_detections(full_out[lo:hi].clone(), full_cnt[lo:hi].clone())
     ok = torch.equal(out, full_out) and torch.equal(cnt, full_cnt)
     lst = R.to_list(out, cnt)
@@ -30,6 +31,15 @@ def _worker(rank, world, port, ret):
     lo, hi = R.shard_bounds(n7, rank, world)
     out7, cnt7 = R.gather_detections(f_out[lo:hi].clone(), f_cnt[lo:hi].clone(), n_images=n7)
     ok = ok and torch.equal(out7, f_out) and torch.equal(cnt7, f_cnt)
+    # fused-payload gatherer (rows + counts in one collective, double buffered); on CPU tensors it runs synchronously
+    gat = R.DetectionGatherer(hi0 - lo0, max_det, 'cpu')
+    for step in range(3):
+        o, c = gat.slot(step)
+        o.copy_(full_out[lo0:hi0] + step)
+        c.copy_(full_cnt[lo0:hi0])
+        gat.launch(step)
+        go, gc = gat.result(step)
+        ok = ok and torch.equal(go.reshape(n_images, max_det, 6), full_out + step) and torch.equal(gc.reshape(-1), full_cnt)
     ret[rank] = bool(ok)
     dist.destroy_process_group()
 
