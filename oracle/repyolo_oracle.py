@@ -714,6 +714,15 @@ def decode_heads(head_maps, anchor_grid, strides=STRIDES, na=3):
     return torch.cat(z, 1), raws
 
 
+def convert(pred):
+    """IDetect.convert (models/yolo.py:189-199): the ``include_nms`` output contract -- boxes xywh -> xyxy through the
+    4x4 matrix, score = cls * obj.  pred: [B, N, 5+nc] (the concatenated decode).  Returns (box [B,N,4], score [B,N,nc])."""
+    box, conf, score = pred[:, :, :4], pred[:, :, 4:5], pred[:, :, 5:]
+    score = score * conf
+    m = torch.tensor([[1, 0, 1, 0], [0, 1, 0, 1], [-0.5, 0, 0.5, 0], [0, -0.5, 0, 0.5]], dtype=torch.float32)
+    return box @ m, score
+
+
 def forward_fused(fz, layers, save, x):
     """Deploy forward.  Returns (outs, pred, raws): outs[i] = layer i output (outs[-1] = 3 raw head conv maps)."""
     with torch.no_grad():

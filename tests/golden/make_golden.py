@@ -14,6 +14,9 @@ What it does
      the decoded prediction and the raw head tensors                    -> layers_64.npz, layers_64x96.npz
   4. runs the reference ``utils.general.non_max_suppression`` on synthetic candidate sets (ties, zero-area boxes,
      empty images, multi-label, agnostic, class filter, > max_nms rows)   -> nms_cases.npz
+  5. runs the reference head with ``include_nms`` (IDetect.convert(), models/yolo.py:189-199) and ``end2end`` set on
+     the same 64x64 input                                               -> convert_64.npz
+     (``python tests/golden/make_golden.py --only-convert`` regenerates just this file)
 """
 import contextlib
 import io
@@ -119,6 +122,22 @@ def main():
         json.dump(keys, f)
     np.savez_compressed(os.path.join(HERE, 'fold_digest.npz'),
                         **{k: digest(v) for k, v in fsd.items() if v.dtype.is_floating_point})
+
+    # 5. alternative output contracts of IDetect.fuseforward (yolo.py:158-166) on the tag-'64' input
+    x = torch.rand(1, 3, 64, 64, generator=torch.Generator().manual_seed(5))
+    det = m.model[-1]
+    with torch.no_grad():
+        det.include_nms = True
+        (box, score), = m(x)
+        det.include_nms, det.end2end = False, True
+        e2e = m(x)
+        det.end2end = False
+        pred_plain, _ = m(x)
+    np.savez_compressed(os.path.join(HERE, 'convert_64.npz'), x=x.numpy(), box=box.numpy(), score=score.numpy(), end2end=e2e.numpy(),
+                        pred=pred_plain.numpy())
+    print('convert_64.npz', tuple(box.shape), tuple(score.shape), tuple(e2e.shape))
+    if '--only-convert' in sys.argv:
+        return
 
     for tag, (h, w), seed in (('64', (64, 64), 5), ('64x96', (64, 96), 6)):
         x = torch.rand(1, 3, h, w, generator=torch.Generator().manual_seed(seed))

@@ -113,3 +113,17 @@ def test_greedy_nms_bit_exact_vs_torchvision_cpu():
         got = nms_oracle.greedy_nms(boxes.numpy(), scores.numpy(), thr)
         assert np.array_equal(ref, got), (n, thr, quant)
         assert np.array_equal(ref[:300], nms_oracle.greedy_nms(boxes.numpy(), scores.numpy(), thr, 300))
+
+
+def test_convert_and_end2end_contracts_match_reference(oracle_model):
+    """include_nms -> IDetect.convert() (models/yolo.py:189-199) and end2end -> cat(z) (yolo.py:160-161): the oracle's
+    restatement on the reference's own head inputs reproduces the reference-minted fixture bit for bit."""
+    layers, save, sd, fz = oracle_model
+    g = np.load(os.path.join(GOLDEN, 'convert_64.npz'))
+    lay = np.load(os.path.join(GOLDEN, 'layers_64.npz'))
+    feats = [torch.from_numpy(lay[f'layer{i}']) for i in (62, 63, 64)]
+    pred, _ = O.decode_heads(O.run_fused_layer(fz, layers[-1], feats), fz['model.65.anchor_grid'])
+    assert rel_l2(pred, torch.from_numpy(g['pred'])) <= 1e-6
+    box, score = O.convert(torch.from_numpy(g['pred']))
+    assert np.array_equal(box.numpy(), g['box']) and np.array_equal(score.numpy(), g['score'])
+    assert np.array_equal(g['end2end'], g['pred'])
