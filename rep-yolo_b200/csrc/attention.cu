@@ -61,77 +61,90 @@ __device__ __forceinline__ float v_of(float x, float wv, float bv, float s1, flo
     return relu6_f(fmaf(s1, silu_f(fmaf(wv, x, bv)), t1));
 }
 
-// ---- operand preparation: one elementwise pass per attention module ----
-// For every pixel and channel group d (the 8 input channels of q/k output channel d = the 8 value channels 8d..8d+7):
+// ---- operand computation, fused into the line kernels' staging ----
+// For every line position and channel group d (the 8 input channels of q/k output channel d = the 8 value channels 8d..8d+7):
 //   q = ReLU6(bn(SiLU(gconv_q(x)))), k likewise with the SAME bn (common.py:3693-3701), v = ReLU6(bn1(SiLU(wv*x + bv)))
-// written as the line kernels' shared-memory operand rows (bf16):
-//   QA[pix] = [Qhi | Qhi | Qlo | 0],  KB[pix] = [Khi | Klo | Khi | 0]   (KQ = 3*Cq padded to 16)   ->  QA.KB^T = Qhi.Khi + Qhi.Klo + Qlo.Khi
-//   V[pix]  = v[0..C)
-// so the row / column / energy / value passes stage their operands with plain 16-byte async copies.  A thread keeps the
-// constants of its group d in registers (blockDim % Cq == 0); q/k rows are assembled in shared memory and stored coalesced.
-constexpr int kPrepThreads = 256, kPrepUnroll = 4;
+// written straight into the shared-memory operand rows of the line's two matrix products (bf16):
+//   Aq[pos] = [Qhi | Qhi | Qlo | 0],  Bk[pos] = [Khi | Klo | Khi | 0]   (KQ = 3*Cq padded to 16)   ->  Aq.Bk^T = Qhi.Khi + Qhi.Klo + Qlo.Khi
+//   Vs[pos] = v[0..C)
+// One 16-byte load of x per (position, group) is everything a line pass reads for its operands: the former preparation
+// kernel and its QA / KB / V round trip through HBM (3.1x the bytes of x per module) are gone.  A thread keeps the
+// constants of its group d in registers (threads per line % Cq == 0).  Rows >= L are zero.
+struct AttnW {
+    const float *qk, *wv, *bv, *s1, *t1;
+};
 
-__global__ void __launch_bounds__(kPrepThreads) attn_prep_kernel(const AttnParams p, int KQ, size_t npix, __nv_bfloat16 *__restrict__ QA,
-                                                                 __nv_bfloat16 *__restrict__ KB, __nv_bfloat16 *__restrict__ V) {
-    pdl_trigger();
-    extern __shared__ __align__(16) uint8_t prep_smem[];
-    const int Cq = p.Cq, C = p.C;
-    const int ppb = kPrepThreads / Cq;                                   // pixels per block iteration
-    __nv_bfloat16 *sQ = reinterpret_cast<__nv_bfloat16 *>(prep_smem), *sK = sQ + (size_t)kPrepUnroll * ppb * KQ;
-    const int d = threadIdx.x % Cq, pl = threadIdx.x / Cq;
-    const float *wq = p.qk, *bq = wq + Cq * 8, *wk = bq + Cq, *bk = wk + Cq * 8, *qs = bk + Cq, *qt = qs + Cq;
+struct Geom {
+    int L, LP, KQ;              // line length, padded to 16, padded 3*Cq contraction length
+    int sq, sv, sp;             // row strides (elements) of Aq/Bk, Vs, Ps
+    size_t stats_off, e_off;    // byte offsets in the scratch region: fp32 (max, sum) of the row pass, bf16 vertical energies
+};
+
+template <bool QK, bool VV, typename Src>
+__device__ __forceinline__ void stage_operands(const AttnW &w, int Cq, const Geom &gm, int LP, int tis, int nthr, Src src,
+                                               __nv_bfloat16 *Aq, __nv_bfloat16 *Bk, __nv_bfloat16 *Vs) {
+    const int d = tis % Cq, r0 = tis / Cq, rstep = nthr / Cq;
     float rwq[8], rwk[8], rwv[8], rbv[8], rs1[8], rt1[8];
+    float rbq = 0.0f, rbk = 0.0f, sc = 0.0f, sh = 0.0f;
+    if (QK) {
+        const float *wq = w.qk, *bq = wq + Cq * 8, *wk = bq + Cq, *bk = wk + Cq * 8, *qs = bk + Cq, *qt = qs + Cq;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        rwq[j] = __ldg(wq + d * 8 + j); rwk[j] = __ldg(wk + d * 8 + j);
-        rwv[j] = __ldg(p.wv + d * 8 + j); rbv[j] = __ldg(p.bv + d * 8 + j);
-        rs1[j] = __ldg(p.s1 + d * 8 + j); rt1[j] = __ldg(p.t1 + d * 8 + j);
+        for (int j = 0; j < 8; ++j) { rwq[j] = __ldg(wq + d * 8 + j); rwk[j] = __ldg(wk + d * 8 + j); }
+        rbq = __ldg(bq + d); rbk = __ldg(bk + d); sc = __ldg(qs + d); sh = __ldg(qt + d);
     }
-    const float rbq = __ldg(bq + d), rbk = __ldg(bk + d), sc = __ldg(qs + d), sh = __ldg(qt + d);
-    for (int i = threadIdx.x; i < 2 * kPrepUnroll * ppb * KQ / 8; i += kPrepThreads) reinterpret_cast<uint4 *>(prep_smem)[i] = make_uint4(0, 0, 0, 0);   // K padding
-    pdl_wait();
-    __syncthreads();
-    const int rowv = KQ / 8;                                             // 16-byte vectors per operand row
-    const int rows_it = kPrepUnroll * ppb;                               // pixels per block iteration
-    for (size_t p0 = (size_t)blockIdx.x * rows_it; p0 < npix; p0 += (size_t)gridDim.x * rows_it) {
-        uint4 u[kPrepUnroll];
+    if (VV) {
 #pragma unroll
-        for (int r = 0; r < kPrepUnroll; ++r) {                          // all loads in flight before the math
-            const size_t pix = p0 + pl + (size_t)r * ppb;
-            u[r] = pix < npix ? __ldg(reinterpret_cast<const uint4 *>(p.x + pix * p.x_cs + p.x_off + d * 8)) : make_uint4(0, 0, 0, 0);
+        for (int j = 0; j < 8; ++j) {
+            rwv[j] = __ldg(w.wv + d * 8 + j); rbv[j] = __ldg(w.bv + d * 8 + j);
+            rs1[j] = __ldg(w.s1 + d * 8 + j); rt1[j] = __ldg(w.t1 + d * 8 + j);
+        }
+    }
+    const int npad = gm.KQ - 3 * Cq;                               // 0, 4 or 8 zero columns behind the three Cq-wide parts
+    constexpr int U = 4;
+    for (int pb = r0; pb < LP; pb += U * rstep) {
+        uint4 u[U];
+#pragma unroll
+        for (int r = 0; r < U; ++r) {                                // all loads in flight before the math
+            const int pi = pb + r * rstep;
+            u[r] = pi < gm.L ? src(pi, d) : make_uint4(0, 0, 0, 0);
         }
 #pragma unroll
-        for (int r = 0; r < kPrepUnroll; ++r) {
-            const size_t pix = p0 + pl + (size_t)r * ppb;
-            if (pix >= npix) continue;
+        for (int r = 0; r < U; ++r) {
+            const int pi = pb + r * rstep;
+            if (pi >= LP) break;
+            const bool ok = pi < gm.L;
             const float2 f0 = unpack_bf16x2(u[r].x), f1 = unpack_bf16x2(u[r].y), f2 = unpack_bf16x2(u[r].z), f3 = unpack_bf16x2(u[r].w);
             const float xv[8] = {f0.x, f0.y, f1.x, f1.y, f2.x, f2.y, f3.x, f3.y};
-            float aq = rbq, ak = rbk;
+            if (QK) {
+                float qa = 0.0f, kb = 0.0f;
+                if (ok) {
+                    float aq = rbq, ak = rbk;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                aq = fmaf(rwq[j], xv[j], aq);
-                ak = fmaf(rwk[j], xv[j], ak);
+                    for (int j = 0; j < 8; ++j) {
+                        aq = fmaf(rwq[j], xv[j], aq);
+                        ak = fmaf(rwk[j], xv[j], ak);
+                    }
+                    qa = relu6_f(fmaf(sc, silu_f(aq), sh));
+                    kb = relu6_f(fmaf(sc, silu_f(ak), sh));
+                }
+                const __nv_bfloat16 qh = __float2bfloat16_rn(qa), kh = __float2bfloat16_rn(kb);
+                const __nv_bfloat16 ql = __float2bfloat16_rn(qa - __bfloat162float(qh)), kl = __float2bfloat16_rn(kb - __bfloat162float(kh));
+                __nv_bfloat16 *ar = Aq + (size_t)pi * gm.sq, *br = Bk + (size_t)pi * gm.sq;
+                ar[d] = qh; ar[Cq + d] = qh; ar[2 * Cq + d] = ql;
+                br[d] = kh; br[Cq + d] = kl; br[2 * Cq + d] = kh;
+                if (d < npad) ar[3 * Cq + d] = br[3 * Cq + d] = __float2bfloat16_rn(0.0f);
             }
-            const float qa = relu6_f(fmaf(sc, silu_f(aq), sh)), kb = relu6_f(fmaf(sc, silu_f(ak), sh));
-            uint32_t ow[4];
+            if (VV) {
+                uint32_t ow[4] = {0u, 0u, 0u, 0u};
+                if (ok) {
 #pragma unroll
-            for (int h = 0; h < 4; ++h)
-                ow[h] = pack_bf16x2(v_of(xv[2 * h], rwv[2 * h], rbv[2 * h], rs1[2 * h], rt1[2 * h]),
-                                    v_of(xv[2 * h + 1], rwv[2 * h + 1], rbv[2 * h + 1], rs1[2 * h + 1], rt1[2 * h + 1]));
-            *reinterpret_cast<uint4 *>(V + pix * C + d * 8) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-            const __nv_bfloat16 qh = __float2bfloat16_rn(qa), kh = __float2bfloat16_rn(kb);
-            const __nv_bfloat16 ql = __float2bfloat16_rn(qa - __bfloat162float(qh)), kl = __float2bfloat16_rn(kb - __bfloat162float(kh));
-            __nv_bfloat16 *ar = sQ + (size_t)(pl + r * ppb) * KQ, *br = sK + (size_t)(pl + r * ppb) * KQ;
-            ar[d] = qh; ar[Cq + d] = qh; ar[2 * Cq + d] = ql;
-            br[d] = kh; br[Cq + d] = kl; br[2 * Cq + d] = kh;
+                    for (int h = 0; h < 4; ++h)
+                        ow[h] = pack_bf16x2(v_of(xv[2 * h], rwv[2 * h], rbv[2 * h], rs1[2 * h], rt1[2 * h]),
+                                            v_of(xv[2 * h + 1], rwv[2 * h + 1], rbv[2 * h + 1], rs1[2 * h + 1], rt1[2 * h + 1]));
+                }
+                *reinterpret_cast<uint4 *>(Vs + (size_t)pi * gm.sv + d * 8) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+            }
         }
-        __syncthreads();
-        const int nrow = (int)min((size_t)rows_it, npix - p0);
-        for (int i = threadIdx.x; i < nrow * rowv; i += kPrepThreads) {
-            reinterpret_cast<uint4 *>(QA + p0 * KQ)[i] = reinterpret_cast<const uint4 *>(sQ)[i];
-            reinterpret_cast<uint4 *>(KB + p0 * KQ)[i] = reinterpret_cast<const uint4 *>(sK)[i];
-        }
-        __syncthreads();
     }
 }
 

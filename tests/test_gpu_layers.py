@@ -339,3 +339,108 @@ def test_detect_decode_nc2_generic_head():
         assert bool(((a.cpu() - b).abs() <= 2e-4 * (1 + b.abs())).all()), float((a.cpu() - b).abs().max())
     p = pred.cpu()
     assert bool(((p - pred_b).abs() <= 2e-3 + 1e-4 * pred_b.abs()).all()), float((p - pred_b).abs().max())
+
+
+# ---- BASELINE batch sizes (the B=64 code paths -- tile ranges spanning images, the two-image per-image-vector
+# staging, magic-division image indices at 6.5 M pixels, thousands of tiles per persistent CTA -- ran unchecked) ----
+def _arena_put_tiled(eng, view, x4, B):
+    """oracle activations of a few images, tiled along the batch to B images, written into a plan view (GPU-side permute)."""
+    from gpu_util import nchw_to_arena
+    rep = B // x4.shape[0]
+    nchw_to_arena(eng, view, x4.cuda().repeat(rep, *([1] * (x4.dim() - 1))))
+
+
+def _arena_get(eng, view):
+    t, off, n = view
+    src = eng.tensor(t)
+    if src.dim() == 2:
+        return src[:, off:off + n].float().reshape(src.shape[0], n, 1, 1)
+    return src[..., off:off + n].float().permute(0, 3, 1, 2)
+
+
+def _run_groups_tiled(m, layers, outs, x0, B, H, W, n_ref, want_first_layers=None):
+    """Teacher-forced groups at batch B with the oracle's n_ref images repeated B / n_ref times.  Checks (1) images
+    0..n_ref-1 and the LAST n_ref images against the oracle (stated tolerances), (2) every image equals its period-n_ref
+    twin bit for bit (a tile, image index or staging slip at large B shows up as a difference between twins)."""
+    from gpu_util import rel_l2
+    eng = m.engine('cuda:0')
+    eng.bind(B, H, W)
+    report, bad = [], []
+    for g in eng.plan_ir.groups:
+        kind = layers[g.layers[0]]['kind']
+        if kind == 'IDetect' or (want_first_layers is not None and g.layers[0] not in want_first_layers):
+            continue
+        image = None
+        for src, view in g.inputs:
+            if src == -1:
+                image = x0.cuda().repeat(B // n_ref, 1, 1, 1).contiguous()
+            else:
+                _arena_put_tiled(eng, view, outs[src], B)
+        eng.run_ops(g.first_op, g.last_op, image=image)
+        torch.cuda.synchronize()
+        got = _arena_get(eng, g.output)
+        ref = outs[g.out_layer]
+        assert got.shape[1:] == ref.shape[1:] and got.shape[0] == B
+        twins = got.reshape(B // n_ref, n_ref, *got.shape[1:])
+        if not bool((twins == twins[:1]).all()):
+            bad.append((g.layers, kind, 'twin images differ', float((twins - twins[:1]).abs().max())))
+        e_first, e_last = rel_l2(got[:n_ref].cpu(), ref), rel_l2(got[B - n_ref:].cpu(), ref)
+        report.append((g.layers, kind, round(e_first, 5), round(e_last, 5)))
+        if not (e_first <= TOL[kind] and e_last <= TOL[kind]):
+            bad.append((g.layers, kind, e_first, e_last, TOL[kind]))
+        del got, twins
+    print('\nteacher-forced rel-L2 per group at B =', B, report)
+    assert not bad, bad
+    return eng
+
+
+def test_groups_teacher_forced_batch64_640(oracle_model):
+    """BASELINE configs[1]: every lowered group at B = 64 @ 640x640 (oracle on 4 images: the GPU batch is those 4 repeated
+    16 times, checked on images 0-3 and 60-63 + twin equality over all 64), then Detect + decode at B = 64."""
+    import torch.nn.functional as F
+    import repyolo_b200 as R
+    layers, save, sd, fz = oracle_model
+    m = R.Model()
+    m.load_state_dict(sd, strict=True)
+    m.fuse()
+    B, H, W, n_ref = 64, 640, 640, 4
+    x0 = torch.rand(n_ref, 3, H, W, generator=torch.Generator().manual_seed(64))
+    outs, pred_ref, raws_ref = O.forward_fused(fz, layers, save, x0)
+    eng = _run_groups_tiled(m, layers, outs, x0, B, H, W, n_ref)
+    # Detect head + decode (normalised features, see test_detect_decode_teacher_forced)
+    g = eng.plan_ir.groups[-1]
+    feats = [o / o.pow(2).mean().sqrt() for o in (outs[62], outs[63], outs[64])]
+    for (src, view), f in zip(g.inputs, feats):
+        _arena_put_tiled(eng, view, f, B)
+    pred, raws = eng._outputs(B, H, W)
+    eng.run_ops(g.first_op, g.last_op, pred=pred, raws=raws)
+    torch.cuda.synchronize()
+    tw = pred.reshape(B // n_ref, n_ref, *pred.shape[1:])
+    assert bool((tw == tw[:1]).all())
+    heads_b = [F.conv2d(f.bfloat16().float(), fz[f'model.65.m.{j}.weight'].bfloat16().float(), fz[f'model.65.m.{j}.bias'])
+               for j, f in enumerate(feats)]
+    pred_b, raws_b = O.decode_heads(heads_b, fz['model.65.anchor_grid'])
+    for sl in (slice(0, n_ref), slice(B - n_ref, B)):
+        p = pred[sl].cpu()
+        assert bool(((p - pred_b).abs() <= 2e-3 + 1e-4 * pred_b.abs()).all()), float((p - pred_b).abs().max())
+        for a, b in zip(raws, raws_b):
+            assert bool(((a[sl].cpu() - b).abs() <= 2e-4 * (1 + b.abs())).all())
+
+
+def test_der_block_teacher_forced_batch16_1280(oracle_model):
+    """BASELINE configs[3]: DER_Block L1 (+ fused MP) and the stem at B = 16 @ 1280x1280 (oracle on 2 images, tiled 8x)."""
+    import repyolo_b200 as R
+    layers, save, sd, fz = oracle_model
+    m = R.Model()
+    m.load_state_dict(sd, strict=True)
+    m.fuse()
+    B, H, W, n_ref = 16, 1280, 1280, 2
+    x0 = torch.rand(n_ref, 3, H, W, generator=torch.Generator().manual_seed(1280))
+    outs = {}
+    with torch.no_grad():
+        y = O.run_fused_layer(fz, layers[0], x0)
+        outs[0] = y
+        y = O.run_fused_layer(fz, layers[1], y)
+        outs[1] = y
+        outs[2] = O.run_fused_layer(fz, layers[2], y)
+    _run_groups_tiled(m, layers, outs, x0, B, H, W, n_ref, want_first_layers=(0, 1))
