@@ -61,6 +61,36 @@ __device__ __forceinline__ float v_of(float x, float wv, float bv, float s1, flo
     return relu6_f(fmaf(s1, silu_f(fmaf(wv, x, bv)), t1));
 }
 
+// The line kernels are instruction-issue bound (ncu: 58 % issue slots busy at 22 % occupancy, DRAM < 15 %), and two thirds of
+// their instructions were the range-checked expansions of __expf / __fdividef in the operand staging.  Raw MUFU forms:
+constexpr float kLog2e = 1.4426950408889634f;
+__device__ __forceinline__ float ex2_fast(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_fast(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float tanh_fast(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// q / k feed a soft-max: full-precision SiLU (two MUFU, ~2^-22 each)
+__device__ __forceinline__ float silu_mufu(float x) { return x * rcp_fast(1.0f + ex2_fast(-kLog2e * x)); }
+// v is rounded to bf16 right away: SiLU(z) = h + h*tanh(h), h = z/2 (one MUFU, |error| <= |h| * 2^-11), the 1/2 folded into wv, bv
+__device__ __forceinline__ float v_fast(float x, float wv_h, float bv_h, float s1, float t1) {
+    const float h = fmaf(wv_h, x, bv_h);
+    return relu6_f(fmaf(s1, fmaf(h, tanh_fast(h), h), t1));
+}
+__device__ __forceinline__ void ldg8(float (&r)[8], const float *p) {
+    const float4 a = __ldg(reinterpret_cast<const float4 *>(p)), b = __ldg(reinterpret_cast<const float4 *>(p) + 1);
+    r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w; r[4] = b.x; r[5] = b.y; r[6] = b.z; r[7] = b.w;
+}
+
 // ---- operand computation, fused into the line kernels' staging ----
 // For every line position and channel group d (the 8 input channels of q/k output channel d = the 8 value channels 8d..8d+7):
 //   q = ReLU6(bn(SiLU(gconv_q(x)))), k likewise with the SAME bn (common.py:3693-3701), v = ReLU6(bn1(SiLU(wv*x + bv)))
@@ -88,16 +118,17 @@ __device__ __forceinline__ void stage_operands(const AttnW &w, int Cq, const Geo
     float rbq = 0.0f, rbk = 0.0f, sc = 0.0f, sh = 0.0f;
     if (QK) {
         const float *wq = w.qk, *bq = wq + Cq * 8, *wk = bq + Cq, *bk = wk + Cq * 8, *qs = bk + Cq, *qt = qs + Cq;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { rwq[j] = __ldg(wq + d * 8 + j); rwk[j] = __ldg(wk + d * 8 + j); }
+        ldg8(rwq, wq + d * 8);                                    // (every array of the pack starts 16-byte aligned: Cq % 4 == 0)
+        ldg8(rwk, wk + d * 8);
         rbq = __ldg(bq + d); rbk = __ldg(bk + d); sc = __ldg(qs + d); sh = __ldg(qt + d);
     }
     if (VV) {
+        ldg8(rwv, w.wv + d * 8);
+        ldg8(rbv, w.bv + d * 8);
+        ldg8(rs1, w.s1 + d * 8);
+        ldg8(rt1, w.t1 + d * 8);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            rwv[j] = __ldg(w.wv + d * 8 + j); rbv[j] = __ldg(w.bv + d * 8 + j);
-            rs1[j] = __ldg(w.s1 + d * 8 + j); rt1[j] = __ldg(w.t1 + d * 8 + j);
-        }
+        for (int j = 0; j < 8; ++j) { rwv[j] *= 0.5f; rbv[j] *= 0.5f; }
     }
     const int npad = gm.KQ - 3 * Cq;                               // 0, 4 or 8 zero columns behind the three Cq-wide parts
     constexpr int U = 4;
@@ -124,8 +155,8 @@ __device__ __forceinline__ void stage_operands(const AttnW &w, int Cq, const Geo
                         aq = fmaf(rwq[j], xv[j], aq);
                         ak = fmaf(rwk[j], xv[j], ak);
                     }
-                    qa = relu6_f(fmaf(sc, silu_f(aq), sh));
-                    kb = relu6_f(fmaf(sc, silu_f(ak), sh));
+                    qa = relu6_f(fmaf(sc, silu_mufu(aq), sh));
+                    kb = relu6_f(fmaf(sc, silu_mufu(ak), sh));
                 }
                 const __nv_bfloat16 qh = __float2bfloat16_rn(qa), kh = __float2bfloat16_rn(kb);
                 const __nv_bfloat16 ql = __float2bfloat16_rn(qa - __bfloat162float(qh)), kl = __float2bfloat16_rn(kb - __bfloat162float(kh));
@@ -139,8 +170,8 @@ __device__ __forceinline__ void stage_operands(const AttnW &w, int Cq, const Geo
                 if (ok) {
 #pragma unroll
                     for (int h = 0; h < 4; ++h)
-                        ow[h] = pack_bf16x2(v_of(xv[2 * h], rwv[2 * h], rbv[2 * h], rs1[2 * h], rt1[2 * h]),
-                                            v_of(xv[2 * h + 1], rwv[2 * h + 1], rbv[2 * h + 1], rs1[2 * h + 1], rt1[2 * h + 1]));
+                        ow[h] = pack_bf16x2(v_fast(xv[2 * h], rwv[2 * h], rbv[2 * h], rs1[2 * h], rt1[2 * h]),
+                                            v_fast(xv[2 * h + 1], rwv[2 * h + 1], rbv[2 * h + 1], rs1[2 * h + 1], rt1[2 * h + 1]));
                 }
                 *reinterpret_cast<uint4 *>(Vs + (size_t)pi * gm.sv + d * 8) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
             }
@@ -169,18 +200,50 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, bool o
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16 : 0) : "memory");   // !ok: zero fill
 }
 
-struct Geom {
-    int L, LP, KQ;              // line length, padded to 16, padded 3*Cq contraction length
-    int sq, sv, sp;             // row strides (elements) of Aq/Bk, Vs, Ps
-};
+// E = Aq . Bk^T for the warp's 16 query rows (row0..row0+15), all LP columns
+template <int NT>
+__device__ __forceinline__ void line_energies(float (&e)[NT][4], const __nv_bfloat16 *Aq, const __nv_bfloat16 *Bk, int sq, int KQ, int row0, int lane) {
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) e[nt][0] = e[nt][1] = e[nt][2] = e[nt][3] = 0.0f;
+    const uint32_t a_base = smem_addr(Aq + (size_t)(row0 + (lane & 15)) * sq + (lane >> 4) * 8);
+    const uint32_t b_base = smem_addr(Bk + (size_t)((lane & 7) + ((lane >> 4) << 3)) * sq + ((lane >> 3) & 1) * 8);
+    for (int kt = 0; kt < KQ / 16; ++kt) {
+        uint32_t a0, a1, a2, a3;
+        ldsm_x4(a_base + kt * 32, a0, a1, a2, a3);
+#pragma unroll
+        for (int np = 0; np < NT / 2; ++np) {
+            uint32_t b0, b1, b2, b3;
+            ldsm_x4(b_base + (uint32_t)(np * 16 * sq * 2) + kt * 32, b0, b1, b2, b3);
+            mma_bf16(e[2 * np], a0, a1, a2, a3, b0, b1);
+            mma_bf16(e[2 * np + 1], a0, a1, a2, a3, b2, b3);
+        }
+    }
+}
 
+// raw energies of image column `line` -> bf16 scratch [b][i][j = line][k]; padded k columns are exact zeros (zero Bk rows)
+template <int NT>
+__device__ __forceinline__ void store_energies(const float (&e)[NT][4], __nv_bfloat16 *E, int b, int H, int W, int line, int L, int row0,
+                                               int g, int t4) {
+    constexpr int LP = NT * 8;
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+        const int i = row0 + g + 8 * hh;
+        if (i < L) {
+            uint32_t *dst = reinterpret_cast<uint32_t *>(E + (((size_t)b * H + i) * W + line) * LP) + t4;
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) dst[nt * 4] = pack_bf16x2(e[nt][2 * hh], e[nt][2 * hh + 1]);
+        }
+    }
+}
 
 // LPC lines per CTA (short lines share a CTA for occupancy), one 16-row query tile per warp.  NT = LP / 8 (compile time:
 // register arrays).  Each line slot is an independent "virtual CTA" of NT*16 threads; only __syncthreads is shared.
-template <int MODE, int NT, int LPC>
-__global__ void __launch_bounds__(NT * 16 * LPC) attn_mma_kernel(const AttnParams p, const Geom gm, int total_lines, size_t slot_bytes,
-                                                                 const __nv_bfloat16 *__restrict__ qa, const __nv_bfloat16 *__restrict__ kb,
-                                                                 const __nv_bfloat16 *__restrict__ vv) {
+// FUSE (column pass only): the criss-cross output column just computed is also the input column of the VerticalAttention
+// that follows (CCVA: m1(m(x)), common.py:2654-2655), whose energy pass needs exactly one image column of q/k: it runs
+// here on the column kept in shared memory (w2 = the vertical module's parameters) instead of a launch that re-reads it.
+template <int MODE, int NT, int LPC, bool FUSE>
+__global__ void __launch_bounds__(NT * 16 * LPC) attn_mma_kernel(const AttnParams p, const AttnW w1, const AttnW w2, const Geom gm,
+                                                                 int total_lines, size_t slot_bytes) {
     pdl_trigger();
     pdl_wait();
     extern __shared__ __align__(16) uint8_t sm_all[];
@@ -196,205 +259,189 @@ __global__ void __launch_bounds__(NT * 16 * LPC) attn_mma_kernel(const AttnParam
     __nv_bfloat16 *Bk = Aq + (size_t)LP * sq;
     __nv_bfloat16 *Vs = (MODE == MODE_VPV) ? Aq : Bk + (size_t)LP * sq;      // value pass has no q/k operands
     __nv_bfloat16 *Ps = (MODE == MODE_VE) ? Vs : Vs + (size_t)LP * sv;        // energy pass has no V / P
+    __nv_bfloat16 *Xs = Ps + (size_t)LP * sp;                                 // FUSE: the output column (bf16, rows of sv elements)
     const int lines = (MODE == MODE_ROW) ? p.H : p.W;
     const int b = (active ? vb : 0) / lines, line = (active ? vb : 0) % lines;
     const size_t img = (size_t)b * p.H * p.W;
-    float *row_stats = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(p.scratch) + (((size_t)p.B * p.H * p.W * p.C * 2 + 255) & ~size_t(255)));
+    uint8_t *scratch = reinterpret_cast<uint8_t *>(p.scratch);
+    float *row_stats = reinterpret_cast<float *>(scratch + gm.stats_off);
+    __nv_bfloat16 *Escr = reinterpret_cast<__nv_bfloat16 *>(scratch + gm.e_off);
     const int warp = tis >> 5, lane = tis & 31;
     const int g = lane >> 2, t4 = lane & 3;
     auto pix_of = [&](int i) -> size_t {       // pixel of line position i
         return (MODE == MODE_ROW) ? img + (size_t)line * p.W + i : img + (size_t)i * p.W + line;
     };
+    auto x_src = [&](int pi, int d) -> uint4 {
+        return __ldg(reinterpret_cast<const uint4 *>(p.x + pix_of(pi) * p.x_cs + p.x_off + d * 8));
+    };
 
-    // ---- stage operands: async 16-byte copies of the prepared rows (rows >= L are zero filled) ----
+    // ---- stage operands: q / k / v computed from the line's x values (rows >= L are zero) ----
     if (active) {
-        const uint32_t aq_u = smem_addr(Aq), bk_u = smem_addr(Bk), vs_u = smem_addr(Vs);
-        if (MODE != MODE_VPV) {
-            const int rowv = KQ / 8;
-            for (int idx = tis; idx < LP * rowv; idx += kThreads) {
-                const int pi = idx / rowv, c = idx - pi * rowv;
-                const bool ok = pi < L;
-                const size_t px = ok ? pix_of(pi) : 0;
-                cp_async16(aq_u + (uint32_t)(pi * sq + c * 8) * 2, qa + px * KQ + c * 8, ok);
-                cp_async16(bk_u + (uint32_t)(pi * sq + c * 8) * 2, kb + px * KQ + c * 8, ok);
-            }
-        }
-        if (MODE != MODE_VE) {
-            const int vecs = C / 8;
+        if (MODE == MODE_VPV) {
+            // P[j][k] = E[b][i = line][j][k] (bf16 scratch written by the energy pass), rows j >= L are zero
+            // general H x W (the reference's view chain, common.py:3763-3775): output column n' uses the H energy rows of the
+            // flat pixels n'*H .. n'*H + H-1 (row-major) -- for H == W that is image row n'
+            const __nv_bfloat16 *E = Escr + ((size_t)b * p.H * p.W + (size_t)line * p.H) * LP;
+            const int vecs = LP / 8;
+            const uint32_t ps_u = smem_addr(Ps);
             for (int idx = tis; idx < LP * vecs; idx += kThreads) {
-                const int pi = idx / vecs, c = idx - pi * vecs;
-                const bool ok = pi < L;
-                const size_t px = ok ? pix_of(pi) : 0;
-                cp_async16(vs_u + (uint32_t)(pi * sv + c * 8) * 2, vv + px * C + c * 8, ok);
+                const int j = idx / vecs, c = (idx - j * vecs) * 8;
+                cp_async16(ps_u + (uint32_t)(j * sp + c) * 2, E + (size_t)(j < L ? j : 0) * LP + c, j < L);
             }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            stage_operands<false, true>(w1, p.Cq, gm, LP, tis, kThreads, x_src, Aq, Bk, Vs);
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        } else if (MODE == MODE_VE) {
+            stage_operands<true, false>(w1, p.Cq, gm, LP, tis, kThreads, x_src, Aq, Bk, Vs);
+        } else {
+            stage_operands<true, true>(w1, p.Cq, gm, LP, tis, kThreads, x_src, Aq, Bk, Vs);
         }
     }
-    if (MODE == MODE_VPV && active) {
-        // P[j][k] = E[b][i = line][j][k] (bf16 scratch written by the energy pass), rows j >= L are zero
-        // general H x W (the reference's view chain, common.py:3763-3775): output column n' uses the H energy rows of the
-        // flat pixels n'*H .. n'*H + H-1 (row-major) -- for H == W that is image row n'
-        const __nv_bfloat16 *E = reinterpret_cast<const __nv_bfloat16 *>(p.scratch) + ((size_t)b * p.H * p.W + (size_t)line * p.H) * LP;
-        const int vecs = LP / 8;
-        const uint32_t ps_u = smem_addr(Ps);
-        for (int idx = tis; idx < LP * vecs; idx += kThreads) {
-            const int j = idx / vecs, c = (idx - j * vecs) * 8;
-            cp_async16(ps_u + (uint32_t)(j * sp + c) * 2, E + (size_t)(j < L ? j : 0) * LP + c, j < L);
-        }
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
 
     const int row0 = warp * 16;                                  // this warp's query rows
     float m_row[2] = {0.0f, 0.0f}, s_row[2] = {1.0f, 1.0f};
     if (MODE != MODE_VPV && active) {
-        // ---- E = Aq . Bk^T for rows row0..row0+15, all LP columns ----
         float e[NT][4];
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt) e[nt][0] = e[nt][1] = e[nt][2] = e[nt][3] = 0.0f;
-        const uint32_t a_base = smem_addr(Aq + (size_t)(row0 + (lane & 15)) * sq + (lane >> 4) * 8);
-        const uint32_t b_base = smem_addr(Bk + (size_t)((lane & 7) + ((lane >> 4) << 3)) * sq + ((lane >> 3) & 1) * 8);
-        for (int kt = 0; kt < KQ / 16; ++kt) {
-            uint32_t a0, a1, a2, a3;
-            ldsm_x4(a_base + kt * 32, a0, a1, a2, a3);
-#pragma unroll
-            for (int np = 0; np < NT / 2; ++np) {
-                uint32_t b0, b1, b2, b3;
-                ldsm_x4(b_base + (uint32_t)(np * 16 * sq * 2) + kt * 32, b0, b1, b2, b3);
-                mma_bf16(e[2 * np], a0, a1, a2, a3, b0, b1);
-                mma_bf16(e[2 * np + 1], a0, a1, a2, a3, b2, b3);
-            }
-        }
+        line_energies<NT>(e, Aq, Bk, sq, KQ, row0, lane);
         if (MODE == MODE_VE) {
-            // raw energies -> bf16 scratch [b][i][j = line][k]; padded k columns are exact zeros (zero Bk rows)
-            __nv_bfloat16 *E = reinterpret_cast<__nv_bfloat16 *>(p.scratch);
+            store_energies<NT>(e, Escr, b, p.H, p.W, line, L, row0, g, t4);
+        } else {
+            // ---- soft-max statistics per query row (columns >= L masked), P -> bf16 shared ----
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
-                const int i = row0 + g + 8 * hh;
-                if (i < L) {
-                    uint32_t *dst = reinterpret_cast<uint32_t *>(E + (((size_t)b * p.H + i) * p.W + line) * LP) + t4;
+                float m = -INFINITY;
 #pragma unroll
-                    for (int nt = 0; nt < NT; ++nt) dst[nt * 4] = pack_bf16x2(e[nt][2 * hh], e[nt][2 * hh + 1]);
+                for (int nt = 0; nt < NT; ++nt) {
+                    const int col = nt * 8 + 2 * t4;
+                    if (col < L) m = fmaxf(m, e[nt][2 * hh]);
+                    if (col + 1 < L) m = fmaxf(m, e[nt][2 * hh + 1]);
                 }
+                m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+                m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+                m *= kLog2e;                                     // statistics in the log2 domain: p = 2^(e*log2e - m)
+                float s = 0.0f;
+                const int r = row0 + g + 8 * hh;
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    const int col = nt * 8 + 2 * t4;
+                    const float p0 = col < L ? ex2_fast(fmaf(e[nt][2 * hh], kLog2e, -m)) : 0.0f;
+                    const float p1 = col + 1 < L ? ex2_fast(fmaf(e[nt][2 * hh + 1], kLog2e, -m)) : 0.0f;
+                    s += p0 + p1;
+                    *reinterpret_cast<uint32_t *>(Ps + (size_t)r * sp + col) = pack_bf16x2(p0, p1);
+                }
+                s += __shfl_xor_sync(0xffffffffu, s, 1);
+                s += __shfl_xor_sync(0xffffffffu, s, 2);
+                m_row[hh] = m;
+                s_row[hh] = s;
             }
-            return;
+            __syncwarp();
         }
-        // ---- soft-max statistics per query row (columns >= L masked), P -> bf16 shared ----
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-            float m = -INFINITY;
-#pragma unroll
-            for (int nt = 0; nt < NT; ++nt) {
-                const int col = nt * 8 + 2 * t4;
-                if (col < L) m = fmaxf(m, e[nt][2 * hh]);
-                if (col + 1 < L) m = fmaxf(m, e[nt][2 * hh + 1]);
-            }
-            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
-            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
-            float s = 0.0f;
-            const int r = row0 + g + 8 * hh;
-#pragma unroll
-            for (int nt = 0; nt < NT; ++nt) {
-                const int col = nt * 8 + 2 * t4;
-                const float p0 = col < L ? __expf(e[nt][2 * hh] - m) : 0.0f;
-                const float p1 = col + 1 < L ? __expf(e[nt][2 * hh + 1] - m) : 0.0f;
-                s += p0 + p1;
-                *reinterpret_cast<uint32_t *>(Ps + (size_t)r * sp + col) = pack_bf16x2(p0, p1);
-            }
-            s += __shfl_xor_sync(0xffffffffu, s, 1);
-            s += __shfl_xor_sync(0xffffffffu, s, 2);
-            m_row[hh] = m;
-            s_row[hh] = s;
-        }
-        __syncwarp();
     }
     if (MODE == MODE_VE) return;
     if (MODE != MODE_VPV) __syncthreads();                       // every warp is done with Aq / Bk: the region becomes the epilogue staging
-    if (!active) return;
 
-    // ---- O = P . V in chunks of 32 channels.  Epilogue per chunk through a per-warp staging tile (16 rows x 32 channels bf16,
-    //      in the dead Aq/Bk region; the value pass has its own) so that every global access is a 16-byte vector of one pixel ----
-    __nv_bfloat16 *wst = ((MODE == MODE_VPV) ? Ps + (size_t)LP * sp : Aq) + (size_t)warp * kStageElems;
-    float *wsc = reinterpret_cast<float *>(wst + 16 * kStagePitch);                       // [16] per-row weight of the row partial
-    float a_h[2] = {1.0f, 1.0f};
-    if (MODE == MODE_COL) {
+    if (active) {
+        // ---- O = P . V in chunks of 32 channels.  Epilogue per chunk through a per-warp staging tile (16 rows x 32 channels bf16,
+        //      in the dead Aq/Bk region; the value pass has its own) so that every global access is a 16-byte vector of one pixel ----
+        __nv_bfloat16 *wst = ((MODE == MODE_VPV) ? Ps + (size_t)LP * sp : Aq) + (size_t)warp * kStageElems;
+        float *wsc = reinterpret_cast<float *>(wst + 16 * kStagePitch);                       // [16] per-row weight of the row partial
+        float a_h[2] = {1.0f, 1.0f};
+        if (MODE == MODE_COL) {
 #pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-            const int i = row0 + g + 8 * hh;
-            float aw = 0.0f;
-            if (i < L) {
-                const float2 ms = *reinterpret_cast<const float2 *>(row_stats + pix_of(i) * 2);
-                const float mw = ms.x, sw = ms.y, mh = m_row[hh], sh = s_row[hh];
-                const float m = fmaxf(mh, mw);
-                const float fh = __expf(mh - m), fw = __expf(mw - m);
-                const float inv = 1.0f / (sh * fh + sw * fw);
-                a_h[hh] = fh * inv;
-                aw = fw * inv;
-            }
-            if (t4 == 0) wsc[g + 8 * hh] = aw;
-        }
-    }
-    if (MODE == MODE_ROW && t4 == 0) {
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-            const int i = row0 + g + 8 * hh;
-            if (i < L) *reinterpret_cast<float2 *>(row_stats + pix_of(i) * 2) = make_float2(m_row[hh], s_row[hh]);
-        }
-    }
-    const uint32_t pa_base = smem_addr(Ps + (size_t)(row0 + (lane & 15)) * sp + (lane >> 4) * 8);
-    const uint32_t vb_base = smem_addr(Vs + (size_t)((lane & 7) + ((lane >> 3) & 1) * 8) * sv + (lane >> 4) * 8);
-    for (int c0 = 0; c0 < C; c0 += 32) {
-        float o[4][4];
-#pragma unroll
-        for (int ct = 0; ct < 4; ++ct) o[ct][0] = o[ct][1] = o[ct][2] = o[ct][3] = 0.0f;
-#pragma unroll
-        for (int kt = 0; kt < NT / 2; ++kt) {
-            uint32_t a0, a1, a2, a3;
-            ldsm_x4(pa_base + kt * 32, a0, a1, a2, a3);
-#pragma unroll
-            for (int cp = 0; cp < 2; ++cp) {
-                uint32_t b0, b1, b2, b3;
-                ldsm_x4_trans(vb_base + (uint32_t)(kt * 16 * sv * 2) + (uint32_t)((c0 + cp * 16) * 2), b0, b1, b2, b3);
-                mma_bf16(o[2 * cp], a0, a1, a2, a3, b0, b1);
-                mma_bf16(o[2 * cp + 1], a0, a1, a2, a3, b2, b3);
-            }
-        }
-        __syncwarp();                                            // previous chunk's staging reads are done
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh)
-#pragma unroll
-            for (int ct = 0; ct < 4; ++ct)
-                *reinterpret_cast<uint32_t *>(wst + (g + 8 * hh) * kStagePitch + ct * 8 + 2 * t4) =
-                    pack_bf16x2(o[ct][2 * hh] * a_h[hh], o[ct][2 * hh + 1] * a_h[hh]);
-        __syncwarp();
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const int idx = lane + 32 * k, r = idx >> 2, v = idx & 3;
-            const int i = row0 + r;
-            if (i >= L) continue;
-            const size_t px = pix_of(i);
-            const uint4 oh = *reinterpret_cast<const uint4 *>(wst + r * kStagePitch + v * 8);
-            const int c = c0 + v * 8;
-            if (MODE == MODE_ROW) {
-                // un-normalised row partial O_W as bf16 [pix][C] (it re-enters a bf16 result scaled by gamma)
-                *reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(p.scratch) + px * C + c) = oh;
-            } else {
-                const uint4 xw = __ldg(reinterpret_cast<const uint4 *>(p.x + px * p.x_cs + p.x_off + c));
-                uint4 pw = make_uint4(0, 0, 0, 0);
+            for (int hh = 0; hh < 2; ++hh) {
+                const int i = row0 + g + 8 * hh;
                 float aw = 0.0f;
-                if (MODE == MODE_COL) {
-                    pw = *reinterpret_cast<const uint4 *>(reinterpret_cast<const __nv_bfloat16 *>(p.scratch) + px * C + c);
-                    aw = wsc[r];
+                if (i < L) {
+                    const float2 ms = *reinterpret_cast<const float2 *>(row_stats + pix_of(i) * 2);
+                    const float mw = ms.x, sw = ms.y, mh = m_row[hh], sh = s_row[hh];
+                    const float m = fmaxf(mh, mw);
+                    const float fh = ex2_fast(mh - m), fw = ex2_fast(mw - m);          // (max, sum) of both passes are in the log2 domain
+                    const float inv = 1.0f / (sh * fh + sw * fw);
+                    a_h[hh] = fh * inv;
+                    aw = fw * inv;
                 }
-                const uint32_t ohw[4] = {oh.x, oh.y, oh.z, oh.w}, xww[4] = {xw.x, xw.y, xw.z, xw.w}, pww[4] = {pw.x, pw.y, pw.z, pw.w};
-                uint32_t res[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const float2 fo = unpack_bf16x2(ohw[q]), fx = unpack_bf16x2(xww[q]), fp = unpack_bf16x2(pww[q]);
-                    res[q] = pack_bf16x2(fmaf(p.gamma, fmaf(fp.x, aw, fo.x), fx.x), fmaf(p.gamma, fmaf(fp.y, aw, fo.y), fx.y));
-                }
-                *reinterpret_cast<uint4 *>(p.out + px * p.out_cs + p.out_off + c) = make_uint4(res[0], res[1], res[2], res[3]);
+                if (t4 == 0) wsc[g + 8 * hh] = aw;
             }
+        }
+        if (MODE == MODE_ROW && t4 == 0) {
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const int i = row0 + g + 8 * hh;
+                if (i < L) *reinterpret_cast<float2 *>(row_stats + pix_of(i) * 2) = make_float2(m_row[hh], s_row[hh]);
+            }
+        }
+        const uint32_t pa_base = smem_addr(Ps + (size_t)(row0 + (lane & 15)) * sp + (lane >> 4) * 8);
+        const uint32_t vb_base = smem_addr(Vs + (size_t)((lane & 7) + ((lane >> 3) & 1) * 8) * sv + (lane >> 4) * 8);
+        for (int c0 = 0; c0 < C; c0 += 32) {
+            float o[4][4];
+#pragma unroll
+            for (int ct = 0; ct < 4; ++ct) o[ct][0] = o[ct][1] = o[ct][2] = o[ct][3] = 0.0f;
+#pragma unroll
+            for (int kt = 0; kt < NT / 2; ++kt) {
+                uint32_t a0, a1, a2, a3;
+                ldsm_x4(pa_base + kt * 32, a0, a1, a2, a3);
+#pragma unroll
+                for (int cp = 0; cp < 2; ++cp) {
+                    uint32_t b0, b1, b2, b3;
+                    ldsm_x4_trans(vb_base + (uint32_t)(kt * 16 * sv * 2) + (uint32_t)((c0 + cp * 16) * 2), b0, b1, b2, b3);
+                    mma_bf16(o[2 * cp], a0, a1, a2, a3, b0, b1);
+                    mma_bf16(o[2 * cp + 1], a0, a1, a2, a3, b2, b3);
+                }
+            }
+            __syncwarp();                                            // previous chunk's staging reads are done
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+                for (int ct = 0; ct < 4; ++ct)
+                    *reinterpret_cast<uint32_t *>(wst + (g + 8 * hh) * kStagePitch + ct * 8 + 2 * t4) =
+                        pack_bf16x2(o[ct][2 * hh] * a_h[hh], o[ct][2 * hh + 1] * a_h[hh]);
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const int idx = lane + 32 * k, r = idx >> 2, v = idx & 3;
+                const int i = row0 + r;
+                if (i >= L) continue;
+                const size_t px = pix_of(i);
+                const uint4 oh = *reinterpret_cast<const uint4 *>(wst + r * kStagePitch + v * 8);
+                const int c = c0 + v * 8;
+                if (MODE == MODE_ROW) {
+                    // un-normalised row partial O_W as bf16 [pix][C] (it re-enters a bf16 result scaled by gamma)
+                    *reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(p.scratch) + px * C + c) = oh;
+                } else {
+                    const uint4 xw = __ldg(reinterpret_cast<const uint4 *>(p.x + px * p.x_cs + p.x_off + c));
+                    uint4 pw = make_uint4(0, 0, 0, 0);
+                    float aw = 0.0f;
+                    if (MODE == MODE_COL) {
+                        pw = *reinterpret_cast<const uint4 *>(reinterpret_cast<const __nv_bfloat16 *>(p.scratch) + px * C + c);
+                        aw = wsc[r];
+                    }
+                    const uint32_t ohw[4] = {oh.x, oh.y, oh.z, oh.w}, xww[4] = {xw.x, xw.y, xw.z, xw.w}, pww[4] = {pw.x, pw.y, pw.z, pw.w};
+                    uint32_t res[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float2 fo = unpack_bf16x2(ohw[q]), fx = unpack_bf16x2(xww[q]), fp = unpack_bf16x2(pww[q]);
+                        res[q] = pack_bf16x2(fmaf(p.gamma, fmaf(fp.x, aw, fo.x), fx.x), fmaf(p.gamma, fmaf(fp.y, aw, fo.y), fx.y));
+                    }
+                    const uint4 rv = make_uint4(res[0], res[1], res[2], res[3]);
+                    *reinterpret_cast<uint4 *>(p.out + px * p.out_cs + p.out_off + c) = rv;
+                    if (FUSE) *reinterpret_cast<uint4 *>(Xs + (size_t)i * sv + c) = rv;
+                }
+            }
+        }
+    }
+    if (FUSE) {
+        // ---- VerticalAttention energy pass on the column just written (kept in Xs) ----
+        __syncthreads();                                         // all staging tiles (in the Aq / Bk region) are dead, Xs is complete
+        if (active) {
+            auto xs_src = [&](int pi, int d) -> uint4 { return *reinterpret_cast<const uint4 *>(Xs + (size_t)pi * sv + d * 8); };
+            stage_operands<true, false>(w2, p.Cq, gm, LP, tis, kThreads, xs_src, Aq, Bk, Vs);
+        }
+        __syncthreads();
+        if (active) {
+            float e[NT][4];
+            line_energies<NT>(e, Aq, Bk, sq, KQ, row0, lane);
+            store_energies<NT>(e, Escr, b, p.H, p.W, line, L, row0, g, t4);
         }
     }
 }
@@ -407,35 +454,25 @@ int pick_nt(int L) {
 }
 
 size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
-size_t pass_scratch_bytes(int B, int H, int W, int C);
 
-struct PrepBufs { __nv_bfloat16 *qa, *kb, *v; int KQ; };
-// scratch = [row partials / energies | QA | KB | V]
-PrepBufs prep_bufs(const AttnParams &p) {
-    PrepBufs b;
-    b.KQ = (3 * p.Cq + 15) / 16 * 16;
-    const size_t npix = (size_t)p.B * p.H * p.W;
-    uint8_t *base = reinterpret_cast<uint8_t *>(p.scratch) + align256(pass_scratch_bytes(p.B, p.H, p.W, p.C));
-    b.qa = reinterpret_cast<__nv_bfloat16 *>(base);
-    b.kb = reinterpret_cast<__nv_bfloat16 *>(base + align256(npix * b.KQ * 2));
-    b.v = reinterpret_cast<__nv_bfloat16 *>(base + 2 * align256(npix * b.KQ * 2));
-    return b;
+// scratch = [criss-cross row partials bf16 [B*H*W][C] | fp32 (max, sum) [B*H*W][2] | vertical energies bf16 [B][H][W][LP]]
+// (the fused column pass reads row partials while it writes energies, so the two regions are disjoint)
+struct ScratchLayout { size_t stats, e, total; };
+ScratchLayout scratch_layout(int B, int H, int W, int C) {
+    const size_t npix = (size_t)B * H * W;
+    ScratchLayout s;
+    s.stats = align256(npix * C * 2);
+    s.e = align256(s.stats + npix * 8);
+    s.total = s.e + align256(npix * (size_t)(pick_nt(H) * 8) * 2);
+    return s;
 }
 
-int prep_launch(const AttnParams &p, cudaStream_t st) {
-    if (kPrepThreads % p.Cq != 0 || p.C != p.Cq * 8) return 1;
-    const PrepBufs pb = prep_bufs(p);
-    const size_t npix = (size_t)p.B * p.H * p.W;
-    const int ppb = kPrepUnroll * kPrepThreads / p.Cq;
-    const size_t blocks = (npix + ppb - 1) / ppb;
-    const int grid = (int)std::min<size_t>(blocks, (size_t)num_sms() * 2);   // resident CTAs: the per-group constants are fetched once
-    launch_pdl(attn_prep_kernel, dim3(grid), dim3(kPrepThreads), (size_t)2 * ppb * pb.KQ * 2, st, p, pb.KQ, npix, pb.qa, pb.kb, pb.v);
-    return 0;
-}
+AttnW weights_of(const AttnParams &p) { return AttnW{p.qk, p.wv, p.bv, p.s1, p.t1}; }
 
-template <int MODE, int NT>
-int launch_nt(const AttnParams &p, int L, cudaStream_t st) {
+template <int MODE, int NT, bool FUSE>
+int launch_nt(const AttnParams &p, const AttnW &w2, int L, cudaStream_t st) {
     constexpr int LPC = NT <= 4 ? 4 : (NT <= 8 ? 2 : 1);      // lines per CTA: keep CTAs at >= 4 warps
+    if ((NT * 16) % p.Cq != 0) return 1;                      // staging: a thread owns one channel group
     Geom gm;
     gm.L = L;
     gm.LP = NT * 8;
@@ -443,35 +480,37 @@ int launch_nt(const AttnParams &p, int L, cudaStream_t st) {
     gm.sq = gm.KQ + 8;
     gm.sv = p.C + 8;
     gm.sp = gm.LP + 8;
+    const ScratchLayout sl = scratch_layout(p.B, p.H, p.W, p.C);
+    gm.stats_off = sl.stats;
+    gm.e_off = sl.e;
     size_t smem = 0;
     if (MODE != MODE_VPV) smem += 2 * (size_t)gm.LP * gm.sq * 2;
     if (MODE != MODE_VE) smem += (size_t)gm.LP * gm.sv * 2 + (size_t)gm.LP * gm.sp * 2;
     if (MODE == MODE_VPV) smem += (size_t)(NT / 2) * kStageElems * 2;          // row / column passes stage in the dead q/k operand region
-    if (MODE == MODE_ROW || MODE == MODE_COL) smem = std::max(smem, (size_t)(NT / 2) * kStageElems * 2);
+    if (FUSE) smem += (size_t)gm.LP * gm.sv * 2;                               // the output column kept for the fused energy pass
     smem = (smem + 15) & ~size_t(15);
     if (smem * LPC > 227 * 1024) return 1;
-    if (RY_ENSURE_DYN_SMEM((attn_mma_kernel<MODE, NT, LPC>), 227 * 1024) != cudaSuccess) return 1;
+    if (RY_ENSURE_DYN_SMEM((attn_mma_kernel<MODE, NT, LPC, FUSE>), 227 * 1024) != cudaSuccess) return 1;
     const int lines = (MODE == MODE_ROW) ? p.H : p.W;
     const int total = p.B * lines;
-    const PrepBufs pb = prep_bufs(p);
-    launch_pdl(attn_mma_kernel<MODE, NT, LPC>, dim3((total + LPC - 1) / LPC), dim3(NT * 16 * LPC), smem * LPC, st, p, gm, total, smem,
-               (const __nv_bfloat16 *)pb.qa, (const __nv_bfloat16 *)pb.kb, (const __nv_bfloat16 *)pb.v);
+    launch_pdl(attn_mma_kernel<MODE, NT, LPC, FUSE>, dim3((total + LPC - 1) / LPC), dim3(NT * 16 * LPC), smem * LPC, st, p, weights_of(p), w2,
+               gm, total, smem);
     return 0;
 }
 
-template <int MODE>
-int launch_mode(const AttnParams &p, cudaStream_t st) {
+template <int MODE, bool FUSE>
+int launch_mode(const AttnParams &p, const AttnW &w2, cudaStream_t st) {
     const int L = (MODE == MODE_ROW) ? p.W : p.H;
-    if (p.C % 32 != 0) return 1;
+    if (p.C % 32 != 0 || p.C != p.Cq * 8) return 1;
     switch (pick_nt(L)) {
-        case 2: return launch_nt<MODE, 2>(p, L, st);
-        case 4: return launch_nt<MODE, 4>(p, L, st);
-        case 6: return launch_nt<MODE, 6>(p, L, st);
-        case 8: return launch_nt<MODE, 8>(p, L, st);
-        case 10: return launch_nt<MODE, 10>(p, L, st);
-        case 12: return launch_nt<MODE, 12>(p, L, st);
-        case 16: return launch_nt<MODE, 16>(p, L, st);
-        case 20: return launch_nt<MODE, 20>(p, L, st);
+        case 2: return launch_nt<MODE, 2, FUSE>(p, w2, L, st);
+        case 4: return launch_nt<MODE, 4, FUSE>(p, w2, L, st);
+        case 6: return launch_nt<MODE, 6, FUSE>(p, w2, L, st);
+        case 8: return launch_nt<MODE, 8, FUSE>(p, w2, L, st);
+        case 10: return launch_nt<MODE, 10, FUSE>(p, w2, L, st);
+        case 12: return launch_nt<MODE, 12, FUSE>(p, w2, L, st);
+        case 16: return launch_nt<MODE, 16, FUSE>(p, w2, L, st);
+        case 20: return launch_nt<MODE, 20, FUSE>(p, w2, L, st);
         default: return 1;
     }
 }
@@ -488,32 +527,26 @@ void attn_qk_launch(const __nv_bfloat16 *x, int x_cs, int x_off, int C, int Cq, 
     launch_pdl(attn_qk_kernel, dim3((int)g), dim3(256), 0, st, x, x_cs, x_off, Cq, npix, wq, bq, wk, bk, s, t, q, k);
 }
 
-// crisscross: [B*H*W][C] bf16 row-pass partials + [B*H*W][2] fp32 statistics; vertical: [B][H][W][LP] bf16 energies -- one
-// shared region, followed by the prepared operands QA | KB | V
-namespace {
-size_t pass_scratch_bytes(int B, int H, int W, int C) {
-    const size_t cc = align256((size_t)B * H * W * C * 2) + (size_t)B * H * W * 8;   // bf16 row partials + fp32 (max, sum)
-    const size_t ve = (size_t)B * H * W * (size_t)(pick_nt(H) * 8) * 2;
-    return cc > ve ? cc : ve;
-}
-}  // namespace
+size_t attn_scratch_bytes(int B, int H, int W, int C) { return scratch_layout(B, H, W, C).total; }
 
-size_t attn_scratch_bytes(int B, int H, int W, int C) {
-    const size_t npix = (size_t)B * H * W;
-    const int KQ = (3 * (C / 8) + 15) / 16 * 16;
-    return align256(pass_scratch_bytes(B, H, W, C)) + 2 * align256(npix * KQ * 2) + align256(npix * C * 2);
-}
-
-int crisscross_launch(const AttnParams &p, cudaStream_t st) {
-    if (prep_launch(p, st)) return 1;
-    if (launch_mode<MODE_ROW>(p, st)) return 1;
-    return launch_mode<MODE_COL>(p, st);
+// next != NULL: the VerticalAttention that consumes this module's output (same geometry): its energy pass is fused into the
+// column pass here, and vertical_launch(..., energies_ready = 1) then only runs the value pass.
+int crisscross_launch(const AttnParams &p, const AttnParams *next, int *energies_done, cudaStream_t st) {
+    const AttnW none{nullptr, nullptr, nullptr, nullptr, nullptr};
+    if (energies_done) *energies_done = 0;
+    if (launch_mode<MODE_ROW, false>(p, none, st)) return 1;
+    if (next != nullptr && energies_done != nullptr && next->C == p.C && next->H == p.H && next->W == p.W && next->B == p.B &&
+        launch_mode<MODE_COL, true>(p, weights_of(*next), st) == 0) {                  // (does not fit shared memory: unfused below)
+        *energies_done = 1;
+        return 0;
+    }
+    return launch_mode<MODE_COL, false>(p, none, st);
 }
 
-int vertical_launch(const AttnParams &p, cudaStream_t st) {
-    if (prep_launch(p, st)) return 1;
-    if (launch_mode<MODE_VE>(p, st)) return 1;
-    return launch_mode<MODE_VPV>(p, st);
+int vertical_launch(const AttnParams &p, int energies_ready, cudaStream_t st) {
+    const AttnW none{nullptr, nullptr, nullptr, nullptr, nullptr};
+    if (!energies_ready && launch_mode<MODE_VE, false>(p, none, st)) return 1;
+    return launch_mode<MODE_VPV, false>(p, none, st);
 }
 
 }  // namespace ry

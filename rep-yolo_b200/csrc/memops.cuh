@@ -37,13 +37,15 @@ struct AttnParams {
     float gamma;
     __nv_bfloat16 *out;       // output map view
     int out_cs, out_off;
-    float *scratch;           // criss-cross: row partials [B*H*W, C] bf16 + (max, sum) fp32; vertical: energies [B,H,W,LP] bf16; then QA | KB | V
+    float *scratch;           // row partials [B*H*W, C] bf16 | (max, sum) fp32 [B*H*W, 2] | vertical energies [B,H,W,LP] bf16
 };
 void attn_qk_launch(const __nv_bfloat16 *x, int x_cs, int x_off, int C, int Cq, size_t npix, const float *wq,
                     const float *bq, const float *wk, const float *bk, const float *s, const float *t, float *q, float *k,
                     cudaStream_t st);
-int crisscross_launch(const AttnParams &p, cudaStream_t st);
-int vertical_launch(const AttnParams &p, cudaStream_t st);
-size_t attn_scratch_bytes(int B, int H, int W, int C);   // row partials / energies + prepared operands QA, KB, V
+// next: the VerticalAttention fed by this module's output (CCVA: m1(m(x))) or NULL; *energies_done = 1 when its energy pass
+// ran fused in the column pass (vertical_launch(..., energies_ready = 1) then runs the value pass only)
+int crisscross_launch(const AttnParams &p, const AttnParams *next, int *energies_done, cudaStream_t st);
+int vertical_launch(const AttnParams &p, int energies_ready, cudaStream_t st);
+size_t attn_scratch_bytes(int B, int H, int W, int C);   // row partials + statistics + energies
 
 }  // namespace ry

@@ -104,6 +104,7 @@ struct ry_plan {
     // optional per-op CUDA-event timing (bench.py roofline): events[2*i], events[2*i+1] bracket op i
     int image_u8 = 0;            // ry_plan_set_image_dtype: the `image` pointer is uint8 NCHW (0..255), /255 fused in the stem
     bool profiling = false;
+    int energies_ready_op = -1;      // index of the VERTICAL op whose energies the preceding fused criss-cross column pass wrote
     std::vector<cudaEvent_t> events;
 };
 
@@ -594,7 +595,8 @@ int bind_chain(ry_plan *p, Op &op, std::vector<CUtensorMap> &maps) {
     return 0;
 }
 
-int run_op(ry_plan *p, Op &op, const float *image, float *pred, float *raws[3], cudaStream_t st) {
+int run_op(ry_plan *p, int idx, int last, const float *image, float *pred, float *raws[3], cudaStream_t st) {
+    Op &op = p->ops[idx];
     const ry_op_desc &d = op.d;
     const int B = p->B;
     switch (d.kind) {
@@ -677,16 +679,39 @@ int run_op(ry_plan *p, Op &op, const float *image, float *pred, float *raws[3], 
         }
         case RY_OP_CRISSCROSS:
         case RY_OP_VERTICAL: {
-            const Tensor &ti = p->tensors[d.in0.tensor], &to = p->tensors[d.out0.tensor];
-            AttnParams ap;
-            ap.x = bf(p, d.in0.tensor); ap.x_cs = ti.d.channels; ap.x_off = d.in0.c_off;
-            ap.C = d.cin; ap.Cq = d.cin / 8; ap.B = B; ap.H = ti.h; ap.W = ti.w;
-            ap.qk = wf(p, op.dev[4]);
-            ap.wv = wf(p, op.dev[0]); ap.bv = wf(p, op.dev[1]); ap.s1 = wf(p, op.dev[2]); ap.t1 = wf(p, op.dev[3]);
-            ap.gamma = d.fparam[0];
-            ap.out = bf(p, d.out0.tensor); ap.out_cs = to.d.channels; ap.out_off = d.out0.c_off;
-            ap.scratch = reinterpret_cast<float *>(p->ws + p->scratch_off);
-            const int rc = d.kind == RY_OP_CRISSCROSS ? crisscross_launch(ap, st) : vertical_launch(ap, st);
+            auto params = [&](const Op &o) {
+                const ry_op_desc &od = o.d;
+                const Tensor &ti = p->tensors[od.in0.tensor], &to = p->tensors[od.out0.tensor];
+                AttnParams ap;
+                ap.x = bf(p, od.in0.tensor); ap.x_cs = ti.d.channels; ap.x_off = od.in0.c_off;
+                ap.C = od.cin; ap.Cq = od.cin / 8; ap.B = B; ap.H = ti.h; ap.W = ti.w;
+                ap.qk = wf(p, o.dev[4]);
+                ap.wv = wf(p, o.dev[0]); ap.bv = wf(p, o.dev[1]); ap.s1 = wf(p, o.dev[2]); ap.t1 = wf(p, o.dev[3]);
+                ap.gamma = od.fparam[0];
+                ap.out = bf(p, od.out0.tensor); ap.out_cs = to.d.channels; ap.out_off = od.out0.c_off;
+                ap.scratch = reinterpret_cast<float *>(p->ws + p->scratch_off);
+                return ap;
+            };
+            const AttnParams ap = params(op);
+            int rc;
+            if (d.kind == RY_OP_CRISSCROSS) {
+                // CCVA = m1(m(x)): when the next op of this run is the VerticalAttention reading this output, its energy pass is
+                // fused into the column pass (the vertical op then only runs its value pass)
+                const Op *nx = (idx + 1 < last) ? &p->ops[idx + 1] : nullptr;
+                const bool feeds = nx && nx->d.kind == RY_OP_VERTICAL && nx->d.in0.tensor == d.out0.tensor && nx->d.in0.c_off == d.out0.c_off &&
+                                   nx->d.in0.c_len == d.out0.c_len && nx->d.cin == d.cin;
+                int done = 0;
+                if (feeds) {
+                    const AttnParams nxp = params(*nx);
+                    rc = crisscross_launch(ap, &nxp, &done, st);
+                } else {
+                    rc = crisscross_launch(ap, nullptr, nullptr, st);
+                }
+                p->energies_ready_op = done ? idx + 1 : -1;
+            } else {
+                rc = vertical_launch(ap, p->energies_ready_op == idx ? 1 : 0, st);
+                p->energies_ready_op = -1;
+            }
             if (rc) RY_FAIL("attention: unsupported shape (shared memory)");
             break;
         }
@@ -877,8 +902,12 @@ int ry_plan_bind(ry_plan *p, int B, int H, int W, void *workspace, size_t worksp
             maps.push_back(m);
         }
         if (op.d.kind == RY_OP_CA) op.launches = 2;                                               // partial sums + finish
-        if (op.d.kind == RY_OP_CRISSCROSS || op.d.kind == RY_OP_VERTICAL) op.launches = 3;         // operand prep + two line passes
+        if (op.d.kind == RY_OP_CRISSCROSS || op.d.kind == RY_OP_VERTICAL) op.launches = 2;         // two line passes
     }
+    for (size_t i = 1; i < p->ops.size(); ++i)                                                    // vertical energy pass fused into the criss-cross column pass
+        if (p->ops[i].d.kind == RY_OP_VERTICAL && p->ops[i - 1].d.kind == RY_OP_CRISSCROSS &&
+            p->ops[i].d.in0.tensor == p->ops[i - 1].d.out0.tensor && p->ops[i].d.in0.c_off == p->ops[i - 1].d.out0.c_off)
+            p->ops[i].launches = 1;
     // Detect rows: level -> anchor -> y -> x (models/yolo.py:152, 166)
     int rows = 0;
     for (Op &op : p->ops)
@@ -930,9 +959,10 @@ int ry_run_ops(ry_plan *p, int first, int last, const float *image, float *pred,
     if (first < 0 || last > (int)p->ops.size() || first > last) RY_FAIL("run_ops: bad op range");
     float *raws[3] = {raw0, raw1, raw2};
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    p->energies_ready_op = -1;
     for (int i = first; i < last; ++i) {
         if (p->profiling) cudaEventRecord(p->events[2 * i], st);
-        if (run_op(p, p->ops[i], image, pred, raws, st)) return 1;
+        if (run_op(p, i, last, image, pred, raws, st)) return 1;
         if (p->profiling) cudaEventRecord(p->events[2 * i + 1], st);
     }
     RY_CUDA(cudaGetLastError());
