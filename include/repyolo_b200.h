@@ -16,6 +16,10 @@
  *   ry_run_ops          <- one top-level module of forward_once (teacher-forced module parity; yolo.py:613)
  *   ry_nms              <- non_max_suppression       utils/general.py:953-1045 (+ xywh2xyxy :265-272,
  *                          torchvision.ops.nms call site :1029)
+ *   ry_decode_filter    <- IDetect.fuseforward (yolo.py:139-156) fused with the first step of non_max_suppression,
+ *                          `xc = prediction[..., 4] > conf_thres` (general.py:961): same launches as ry_forward, the Detect
+ *                          epilogue also leaves the filter result as warp-ballot words
+ *   ry_nms_filtered     <- non_max_suppression consuming those words: ordered (prefix-sum) compaction of the survivors only
  */
 #ifndef REPYOLO_B200_H
 #define REPYOLO_B200_H
@@ -27,7 +31,7 @@
 extern "C" {
 #endif
 
-#define RY_ABI_VERSION 4
+#define RY_ABI_VERSION 5
 
 typedef struct ry_plan ry_plan;
 
@@ -154,6 +158,18 @@ int ry_nms_launch_count(int B, int N, int nc, int multi_label, int *n);   /* ker
 int ry_nms(const float *pred, int B, int N, int nc, float conf_thres, double iou_thres, const int32_t *classes_host,
            int n_classes, int agnostic, int multi_label, int max_det, int max_nms, float *out, int32_t *counts,
            void *workspace, size_t workspace_bytes, void *stream);
+
+/* Fused decode + confidence filter (the reference decodes every candidate, yolo.py:139-156, and only then filters them,
+ * general.py:961-978).  ry_decode_filter == ry_forward (pred / raw heads are materialised as always) and additionally
+ * cand_mask: uint32 [B][(N + 31) / 32], zeroed by the call, bit (i & 31) of word (i >> 5) of image b = pred[b, i, 4] > conf_thres,
+ * written from warp ballots over the decoded tile in the Detect epilogue.  ry_nms_filtered == ry_nms, except that candidates are
+ * found by a prefix sum over the mask words (only rows that passed are read); its conf_thres must be >= the mask's.  Outputs
+ * are byte-identical to ry_nms(pred, ...). */
+int ry_decode_filter(ry_plan *plan, const float *image, float conf_thres, float *pred, float *raw0, float *raw1, float *raw2,
+                     uint32_t *cand_mask, void *stream);
+int ry_nms_filtered(const float *pred, const uint32_t *cand_mask, int B, int N, int nc, float conf_thres, double iou_thres,
+                    const int32_t *classes_host, int n_classes, int agnostic, int multi_label, int max_det, int max_nms, float *out,
+                    int32_t *counts, void *workspace, size_t workspace_bytes, void *stream);
 
 /* ---- the callers either side of the path ----
  * ry_letterbox_u8  <- letterbox  utils/datasets.py:984-1014 (cv2.resize INTER_LINEAR + copyMakeBorder; the shape arithmetic --

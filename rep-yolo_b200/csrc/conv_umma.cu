@@ -443,6 +443,31 @@ __device__ __forceinline__ void epilogue_detect_role(const ConvArgs &p, const Ep
         }
         ptx::bar_sync(1, 256);
         const uint32_t pix0 = (uint32_t)tc.w0;
+        if (p.cand_mask != nullptr) {
+            // fused confidence filter (general.py:961 `prediction[..., 4] > conf_thres`) on the decoded objectness of the staged
+            // tile: a warp = 32 consecutive pixels of one anchor = 32 consecutive rows of pred (inside one image), so its ballot is
+            // (part of) one or two words of the image's candidate mask; lanes of the same word OR their bits with one atomic
+            for (int c = tid; c < na * 128; c += 256) {                  // warp-uniform trip count (na * 128 is a multiple of 32)
+                const int a = c >> 7, r = c & 127;
+                const uint32_t pix = pix0 + (uint32_t)r;
+                bool pass = false;
+                uint32_t widx = 0, bit = 0;
+                if ((int)pix < p.Wo) {
+                    const int b = (int)(((uint64_t)pix * p.div_hw) >> 40);
+                    const int rem = (int)(pix - (uint32_t)b * (uint32_t)p.img_hw);
+                    pass = sp[a * rec + r * no + 4] > p.cand_conf;
+                    const uint32_t i = (uint32_t)(p.row_off + a * p.img_hw + rem);
+                    widx = (uint32_t)b * (uint32_t)p.mask_words + (i >> 5);
+                    bit = 1u << (i & 31);
+                }
+                const uint32_t pm = __ballot_sync(0xffffffffu, pass);
+                if (pass) {
+                    const uint32_t peers = __match_any_sync(pm, widx);
+                    const uint32_t bits = __reduce_or_sync(peers, bit);
+                    if ((peers & ((1u << lane) - 1u)) == 0) atomicOr(p.cand_mask + widx, bits);
+                }
+            }
+        }
         const int b0 = (int)(((uint64_t)pix0 * p.div_hw) >> 40);
         const int rem0 = (int)(pix0 - (uint32_t)b0 * (uint32_t)p.img_hw);
         const bool whole = vec_ok && rem0 + 128 <= p.img_hw && (int)pix0 + 128 <= p.Wo;     // one image, no batch tail

@@ -94,6 +94,9 @@ struct ConvArgs {
     int n_pinned;              // 1: gridDim % n_ntiles == 0 with round-robin tiles, i.e. a CTA only ever sees N tile blockIdx % n_ntiles,
                                //    whose weights may then stay resident in shared memory
     float *pred, *raw;         // Detect outputs
+    uint32_t *cand_mask;       // Detect, optional (ry_decode_filter): `obj > cand_conf` of every decoded candidate as ballot words
+    float cand_conf;           //   [B][mask_words] (bit i & 31 of word i >> 5, i = row of pred inside the image), OR-ed in
+    int mask_words;
     int no, na, row_off, rows_total;
     float det_stride;
     float anchors[6];

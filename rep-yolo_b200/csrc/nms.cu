@@ -64,6 +64,81 @@ __device__ __forceinline__ int block_excl_scan(int v, int *warp_sums, int *total
     return base + x - v;
 }
 
+// ---- candidate filter (general.py:961-1013), shared by the two front ends below ----
+struct Cand {
+    float x1, y1, x2, y2, obj, best;
+    int bj;
+};
+
+// number of output rows of candidate p (0 = filtered out); fills the box / best class on the way
+__device__ __forceinline__ int cand_eval(const float *__restrict__ p, int nc, float conf, int multi_label,
+                                         const int *__restrict__ classes, int n_classes, Cand &c) {
+    c.obj = p[4];
+    if (!(c.obj > conf)) return 0;                                             // general.py:962, 978
+    const float cx = p[0], cy = p[1], w = p[2], h = p[3];
+    c.x1 = __fsub_rn(cx, __fdiv_rn(w, 2.0f));                                  // general.py:268-271
+    c.y1 = __fsub_rn(cy, __fdiv_rn(h, 2.0f));
+    c.x2 = __fadd_rn(cx, __fdiv_rn(w, 2.0f));
+    c.y2 = __fadd_rn(cy, __fdiv_rn(h, 2.0f));
+    int cnt = 0;
+    if (multi_label) {                                                         // general.py:1004-1006
+        for (int j = 0; j < nc; ++j) {
+            const float v = __fmul_rn(p[5 + j], c.obj);
+            bool ok = v > conf;
+            if (ok && n_classes > 0) {
+                ok = false;
+                for (int q = 0; q < n_classes; ++q) ok |= (classes[q] == j);
+            }
+            cnt += ok ? 1 : 0;
+        }
+    } else {                                                                   // general.py:1008-1009
+        c.best = 0.0f;
+        c.bj = 0;
+        for (int j = 0; j < nc; ++j) {
+            const float v = (nc == 1) ? c.obj : __fmul_rn(p[5 + j], c.obj);
+            if (j == 0 || v > c.best) { c.best = v; c.bj = j; }
+        }
+        bool ok = c.best > conf;
+        if (ok && n_classes > 0) {                                             // general.py:1012-1013
+            ok = false;
+            for (int q = 0; q < n_classes; ++q) ok |= (classes[q] == c.bj);
+        }
+        cnt = ok ? 1 : 0;
+    }
+    return cnt;
+}
+
+// writes the rows of a candidate that cand_eval counted (cnt > 0) at ordered position `off`; returns the next position
+__device__ __forceinline__ int cand_emit(const float *__restrict__ p, const Cand &c, int nc, float conf, int multi_label,
+                                         const int *__restrict__ classes, int n_classes, float *__restrict__ R,
+                                         uint32_t *__restrict__ Kb, uint32_t *__restrict__ Ib, int off) {
+    if (multi_label) {
+        for (int j = 0; j < nc; ++j) {
+            const float v = __fmul_rn(p[5 + j], c.obj);
+            bool ok = v > conf;
+            if (ok && n_classes > 0) {
+                ok = false;
+                for (int q = 0; q < n_classes; ++q) ok |= (classes[q] == j);
+            }
+            if (ok) {
+                float *r = R + (size_t)off * 6;
+                r[0] = c.x1; r[1] = c.y1; r[2] = c.x2; r[3] = c.y2; r[4] = v; r[5] = (float)j;
+                Kb[off] = desc_key(v);
+                Ib[off] = (uint32_t)off;
+                ++off;
+            }
+        }
+    } else {
+        float *r = R + (size_t)off * 6;
+        r[0] = c.x1; r[1] = c.y1; r[2] = c.x2; r[3] = c.y2; r[4] = c.best; r[5] = (float)c.bj;
+        Kb[off] = desc_key(c.best);
+        Ib[off] = (uint32_t)off;
+        ++off;
+    }
+    return off;
+}
+
+// front end 1: every row of pred is read and tested, one candidate per thread per trip, ordered (prefix-sum) compaction
 __global__ void __launch_bounds__(kFilterThreads) nms_filter_kernel(const float *__restrict__ pred, int N, int nc,
                                                                     float conf, int multi_label,
                                                                     const int *__restrict__ classes, int n_classes,
@@ -78,67 +153,50 @@ __global__ void __launch_bounds__(kFilterThreads) nms_filter_kernel(const float 
     int base = 0;
     for (int i0 = 0; i0 < N; i0 += blockDim.x) {
         const int i = i0 + threadIdx.x;
-        int cnt = 0;
-        float x1 = 0, y1 = 0, x2 = 0, y2 = 0, obj = 0, best = 0;
-        int bj = 0;
         const float *p = P + (size_t)i * no;
-        if (i < N) {
-            obj = p[4];
-            if (obj > conf) {                                                  // general.py:962, 978
-                const float cx = p[0], cy = p[1], w = p[2], h = p[3];
-                x1 = __fsub_rn(cx, __fdiv_rn(w, 2.0f));                        // general.py:268-271
-                y1 = __fsub_rn(cy, __fdiv_rn(h, 2.0f));
-                x2 = __fadd_rn(cx, __fdiv_rn(w, 2.0f));
-                y2 = __fadd_rn(cy, __fdiv_rn(h, 2.0f));
-                if (multi_label) {                                             // general.py:1004-1006
-                    for (int j = 0; j < nc; ++j) {
-                        const float c = __fmul_rn(p[5 + j], obj);
-                        bool ok = c > conf;
-                        if (ok && n_classes > 0) {
-                            ok = false;
-                            for (int q = 0; q < n_classes; ++q) ok |= (classes[q] == j);
-                        }
-                        cnt += ok ? 1 : 0;
-                    }
-                } else {                                                       // general.py:1008-1009
-                    for (int j = 0; j < nc; ++j) {
-                        const float c = (nc == 1) ? obj : __fmul_rn(p[5 + j], obj);
-                        if (j == 0 || c > best) { best = c; bj = j; }
-                    }
-                    bool ok = best > conf;
-                    if (ok && n_classes > 0) {                                 // general.py:1012-1013
-                        ok = false;
-                        for (int q = 0; q < n_classes; ++q) ok |= (classes[q] == bj);
-                    }
-                    cnt = ok ? 1 : 0;
-                }
-            }
+        Cand c;
+        const int cnt = i < N ? cand_eval(p, nc, conf, multi_label, classes, n_classes, c) : 0;
+        int total;
+        const int off = base + block_excl_scan(cnt, warp_sums, &total);
+        if (cnt > 0) cand_emit(p, c, nc, conf, multi_label, classes, n_classes, R, Kb, Ib, off);
+        base += total;
+    }
+    if (threadIdx.x == 0) counts[b] = base;
+}
+
+// front end 2 (fused decode + filter, ry_decode_filter): the Detect epilogue already evaluated `obj > conf` for every
+// candidate it decoded and left the result as ballot words mask[b][ceil(N / 32)] (bit i & 31 of word i >> 5).  One thread
+// per mask word walks its set bits in index order; the block-wide prefix sum over the words' row counts gives the same
+// ordered compaction as front end 1, but only the rows that passed are ever read.
+__global__ void __launch_bounds__(kFilterThreads) nms_gather_kernel(const float *__restrict__ pred, const uint32_t *__restrict__ mask,
+                                                                    int N, int nc, float conf, int multi_label,
+                                                                    const int *__restrict__ classes, int n_classes, size_t cap,
+                                                                    float *__restrict__ rows, uint32_t *__restrict__ keys,
+                                                                    uint32_t *__restrict__ idx, int *__restrict__ counts) {
+    __shared__ int warp_sums[32];
+    const int b = blockIdx.x, no = 5 + nc, words = (N + 31) >> 5;
+    const float *P = pred + (size_t)b * N * no;
+    const uint32_t *M = mask + (size_t)b * words;
+    float *R = rows + (size_t)b * cap * 6;
+    uint32_t *Kb = keys + (size_t)b * cap, *Ib = idx + (size_t)b * cap;
+    int base = 0;
+    for (int w0 = 0; w0 < words; w0 += blockDim.x) {
+        const int w = w0 + threadIdx.x;
+        const uint32_t bits = w < words ? M[w] : 0u;
+        int cnt = 0;
+        Cand c;
+        for (uint32_t m = bits; m; m &= m - 1) {
+            const int i = 32 * w + __ffs(m) - 1;
+            if (i < N) cnt += cand_eval(P + (size_t)i * no, nc, conf, multi_label, classes, n_classes, c);
         }
         int total;
         int off = base + block_excl_scan(cnt, warp_sums, &total);
-        if (cnt > 0) {
-            if (multi_label) {
-                for (int j = 0; j < nc; ++j) {
-                    const float c = __fmul_rn(p[5 + j], obj);
-                    bool ok = c > conf;
-                    if (ok && n_classes > 0) {
-                        ok = false;
-                        for (int q = 0; q < n_classes; ++q) ok |= (classes[q] == j);
-                    }
-                    if (ok) {
-                        float *r = R + (size_t)off * 6;
-                        r[0] = x1; r[1] = y1; r[2] = x2; r[3] = y2; r[4] = c; r[5] = (float)j;
-                        Kb[off] = desc_key(c);
-                        Ib[off] = (uint32_t)off;
-                        ++off;
-                    }
-                }
-            } else {
-                float *r = R + (size_t)off * 6;
-                r[0] = x1; r[1] = y1; r[2] = x2; r[3] = y2; r[4] = best; r[5] = (float)bj;
-                Kb[off] = desc_key(best);
-                Ib[off] = (uint32_t)off;
-            }
+        for (uint32_t m = bits; m && cnt > 0; m &= m - 1) {
+            const int i = 32 * w + __ffs(m) - 1;
+            if (i >= N) break;
+            const float *p = P + (size_t)i * no;
+            if (cand_eval(p, nc, conf, multi_label, classes, n_classes, c) > 0)
+                off = cand_emit(p, c, nc, conf, multi_label, classes, n_classes, R, Kb, Ib, off);
         }
         base += total;
     }
@@ -489,8 +547,8 @@ int nms_launch_count(int B, int N, int nc, int multi_label) {
     return cap <= (size_t)kSoloMaxCap ? 3 : 1 + 4 * 3 + 1;        // filter, sort (one kernel, or hist / scan / scatter x 4), scan
 }
 
-int nms_run(const float *pred, int B, int N, int nc, float conf, double iou, const int32_t *classes_host, int n_classes,
-            int agnostic, int multi_label, int max_det, int max_nms, float *out, int32_t *counts, void *workspace,
+int nms_run(const float *pred, const uint32_t *cand_mask, int B, int N, int nc, float conf, double iou, const int32_t *classes_host,
+            int n_classes, int agnostic, int multi_label, int max_det, int max_nms, float *out, int32_t *counts, void *workspace,
             size_t workspace_bytes, cudaStream_t st) {
     multi_label = (multi_label && nc > 1) ? 1 : 0;                                         // general.py:970
     const NmsLayout L = nms_layout(B, N, nc, multi_label);
@@ -507,7 +565,10 @@ int nms_run(const float *pred, int B, int N, int nc, float conf, double iou, con
     int *cls = reinterpret_cast<int *>(ws + L.classes);
     if (n_classes > 0) RY_CUDA(cudaMemcpyAsync(cls, classes_host, (size_t)n_classes * 4, cudaMemcpyHostToDevice, st));
 
-    nms_filter_kernel<<<B, kFilterThreads, 0, st>>>(pred, N, nc, conf, multi_label, cls, n_classes, L.cap, rows, k0, i0, cnt);
+    if (cand_mask != nullptr)
+        nms_gather_kernel<<<B, kFilterThreads, 0, st>>>(pred, cand_mask, N, nc, conf, multi_label, cls, n_classes, L.cap, rows, k0, i0, cnt);
+    else
+        nms_filter_kernel<<<B, kFilterThreads, 0, st>>>(pred, N, nc, conf, multi_label, cls, n_classes, L.cap, rows, k0, i0, cnt);
     static const bool no_solo = getenv("RY_NMS_MULTI_SORT") != nullptr;
     const bool solo = !no_solo && L.cap <= (size_t)kSoloMaxCap;
     if (solo) sort_image_kernel<<<B, kSoloThreads, 0, st>>>(k0, i0, k1, i1, cnt, L.cap);      // four passes: the result is back in k0 / i0

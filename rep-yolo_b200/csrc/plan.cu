@@ -104,6 +104,8 @@ struct ry_plan {
     // optional per-op CUDA-event timing (bench.py roofline): events[2*i], events[2*i+1] bracket op i
     int image_u8 = 0;            // ry_plan_set_image_dtype: the `image` pointer is uint8 NCHW (0..255), /255 fused in the stem
     bool profiling = false;
+    uint32_t *filter_mask = nullptr;   // set for the duration of ry_decode_filter
+    float filter_conf = 0.0f;
     int energies_ready_op = -1;      // index of the VERTICAL op whose energies the preceding fused criss-cross column pass wrote
     std::vector<cudaEvent_t> events;
 };
@@ -633,6 +635,9 @@ int run_op(ry_plan *p, int idx, int last, const float *image, float *pred, float
             a.omap = a.wmap;
             a.pred = pred;
             a.raw = raws[d.level_idx];
+            a.cand_mask = p->filter_mask;                        // ry_decode_filter: obj > conf ballots of the decoded candidates
+            a.cand_conf = p->filter_conf;
+            a.mask_words = (p->n_cand + 31) / 32;
             conv_launch(a, op.grid, st);
             break;
         }
@@ -1000,6 +1005,19 @@ int ry_forward(ry_plan *p, const float *image, float *pred, float *raw0, float *
     return ry_run_ops(p, 0, (int)p->ops.size(), image, pred, raw0, raw1, raw2, stream);
 }
 
+int ry_decode_filter(ry_plan *p, const float *image, float conf_thres, float *pred, float *raw0, float *raw1, float *raw2,
+                     uint32_t *cand_mask, void *stream) {
+    if (!p || !p->ws) RY_FAIL("decode_filter: plan not bound");
+    if (!cand_mask) RY_FAIL("decode_filter: NULL candidate mask");
+    const size_t words = (size_t)p->B * (size_t)((p->n_cand + 31) / 32);
+    RY_CUDA(cudaMemsetAsync(cand_mask, 0, words * 4, static_cast<cudaStream_t>(stream)));
+    p->filter_mask = cand_mask;
+    p->filter_conf = conf_thres;
+    const int rc = ry_run_ops(p, 0, (int)p->ops.size(), image, pred, raw0, raw1, raw2, stream);
+    p->filter_mask = nullptr;
+    return rc;
+}
+
 int ry_nms_workspace_bytes(int B, int N, int nc, int multi_label, size_t *bytes) {
     if (!bytes || B <= 0 || N <= 0 || nc <= 0) RY_FAIL("nms_workspace_bytes: bad arguments");
     *bytes = nms_workspace_bytes(B, N, nc, multi_label);
@@ -1016,8 +1034,16 @@ int ry_nms(const float *pred, int B, int N, int nc, float conf_thres, double iou
            int n_classes, int agnostic, int multi_label, int max_det, int max_nms, float *out, int32_t *counts, void *workspace,
            size_t workspace_bytes, void *stream) {
     if (!pred || !out || !counts || !workspace) RY_FAIL("ry_nms: NULL pointer");
-    return nms_run(pred, B, N, nc, conf_thres, iou_thres, classes_host, n_classes, agnostic, multi_label, max_det, max_nms, out,
+    return nms_run(pred, nullptr, B, N, nc, conf_thres, iou_thres, classes_host, n_classes, agnostic, multi_label, max_det, max_nms, out,
                    counts, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int ry_nms_filtered(const float *pred, const uint32_t *cand_mask, int B, int N, int nc, float conf_thres, double iou_thres,
+                    const int32_t *classes_host, int n_classes, int agnostic, int multi_label, int max_det, int max_nms, float *out,
+                    int32_t *counts, void *workspace, size_t workspace_bytes, void *stream) {
+    if (!pred || !cand_mask || !out || !counts || !workspace) RY_FAIL("ry_nms_filtered: NULL pointer");
+    return nms_run(pred, cand_mask, B, N, nc, conf_thres, iou_thres, classes_host, n_classes, agnostic, multi_label, max_det, max_nms,
+                   out, counts, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -132,7 +132,10 @@ class NativeEngine:
             N.check(N.lib().ry_plan_set_image_dtype(self.handle, N.RY_U8 if u8 else N.RY_F32), 'ry_plan_set_image_dtype')
             self._image_u8 = u8
 
-    def forward(self, x):
+    def forward(self, x, conf_filter=None):
+        """``conf_filter``: confidence threshold of the fused decode + filter (ry_decode_filter): the Detect epilogue also
+        records ``obj > conf_filter`` per candidate as ballot words; ``pred`` then carries them (``pred._ry_cand``) and
+        ``non_max_suppression(pred, conf_thres >= conf_filter, ...)`` compacts from the mask instead of re-reading ``pred``."""
         # the library reinterprets the buffer by element type: anything but contiguous fp32 / uint8 NCHW on this device
         # would be read as garbage (and past its end), so it is an error here, never a silent cast
         if x.dtype not in (torch.float32, torch.uint8):
@@ -147,8 +150,15 @@ class NativeEngine:
         pred, raws = self._outputs(B, H, W)
         with torch.cuda.device(self.device):
             st = torch.cuda.current_stream(self.device).cuda_stream
-            N.check(N.lib().ry_forward(self.handle, x.data_ptr(), pred.data_ptr(), raws[0].data_ptr(), raws[1].data_ptr(),
-                                       raws[2].data_ptr(), C.c_void_p(st)), 'ry_forward')
+            if conf_filter is None:
+                N.check(N.lib().ry_forward(self.handle, x.data_ptr(), pred.data_ptr(), raws[0].data_ptr(), raws[1].data_ptr(),
+                                           raws[2].data_ptr(), C.c_void_p(st)), 'ry_forward')
+            else:
+                mask = torch.empty((B, (self.n_cand + 31) // 32), dtype=torch.int32, device=self.device)
+                N.check(N.lib().ry_decode_filter(self.handle, x.data_ptr(), C.c_float(float(conf_filter)), pred.data_ptr(),
+                                                 raws[0].data_ptr(), raws[1].data_ptr(), raws[2].data_ptr(), mask.data_ptr(),
+                                                 C.c_void_p(st)), 'ry_decode_filter')
+                pred._ry_cand = (mask, float(conf_filter), pred.data_ptr())
         return pred, raws
 
     def run_ops(self, first, last, image=None, pred=None, raws=(None, None, None)):
@@ -195,6 +205,10 @@ class IDetect(_Node):
 
 
 class Model(nn.Module):
+    # opt-in fused decode + confidence filter (north_star (c)): set to the conf_thres the following non_max_suppression call
+    # will use (or lower); pred is still fully materialised, detections are identical (see NativeEngine.forward)
+    decode_filter = None
+
     def __init__(self, cfg=None, ch=3, nc=None, anchors=None):
         super().__init__()
         self.traced = False
@@ -271,7 +285,7 @@ class Model(nn.Module):
         x = self._check_input(x)
         if augment:
             return self._forward_augment(x)
-        pred, raws = self.engine(x.device, (x.shape[0], x.shape[2], x.shape[3])).forward(x)
+        pred, raws = self.engine(x.device, (x.shape[0], x.shape[2], x.shape[3])).forward(x, conf_filter=self.decode_filter)
         return self.model[-1]._package(pred, raws)
 
     def load_state_dict(self, state_dict, strict=True, **kw):

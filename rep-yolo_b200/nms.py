@@ -39,10 +39,17 @@ def nms_padded(prediction, conf_thres=0.25, iou_thres=0.45, classes=None, agnost
     ``out`` / ``counts``: optional preallocated contiguous destinations (e.g. views of a gather payload)."""
     if not prediction.is_cuda:
         raise N.NativeError('non_max_suppression: prediction must be a CUDA tensor (no CPU fallback on this path)')
+    # candidate mask left by the fused decode + filter (Model.decode_filter -> ry_decode_filter): usable when it was produced
+    # with a threshold <= this call's (the mask is then a superset of `obj > conf_thres`; every row is re-tested exactly)
+    cand = getattr(prediction, '_ry_cand', None)
     p = prediction.detach()
     if p.dtype != torch.float32 or not p.is_contiguous():
         p = p.float().contiguous()
+        cand = None
     B, n, no = p.shape
+    if cand is not None and not (cand[0].shape == (B, (n + 31) // 32) and cand[0].device == p.device and
+                                 float(np.float32(cand[1])) <= float(np.float32(conf_thres)) and cand[2] == p.data_ptr()):
+        cand = None
     nc = no - 5
     multi_label = bool(multi_label) and nc > 1
     if out is None:
@@ -61,10 +68,13 @@ def nms_padded(prediction, conf_thres=0.25, iou_thres=0.45, classes=None, agnost
     cls = np.ascontiguousarray(np.asarray(classes if classes is not None else [], dtype=np.int32).reshape(-1))
     with torch.cuda.device(p.device):
         st = torch.cuda.current_stream(p.device).cuda_stream
-        N.check(N.lib().ry_nms(p.data_ptr(), B, n, nc, C.c_float(float(np.float32(conf_thres))), C.c_double(float(iou_thres)),
-                               cls.ctypes.data if cls.size else None, int(cls.size), int(bool(agnostic)), int(multi_label),
-                               int(max_det), int(max_nms), out.data_ptr(), counts.data_ptr(), ws.data_ptr(), ws.numel(),
-                               C.c_void_p(st)), 'ry_nms')
+        tail = (C.c_float(float(np.float32(conf_thres))), C.c_double(float(iou_thres)), cls.ctypes.data if cls.size else None,
+                int(cls.size), int(bool(agnostic)), int(multi_label), int(max_det), int(max_nms), out.data_ptr(), counts.data_ptr(),
+                ws.data_ptr(), ws.numel(), C.c_void_p(st))
+        if cand is not None:
+            N.check(N.lib().ry_nms_filtered(p.data_ptr(), cand[0].data_ptr(), B, n, nc, *tail), 'ry_nms_filtered')
+        else:
+            N.check(N.lib().ry_nms(p.data_ptr(), B, n, nc, *tail), 'ry_nms')
     return out, counts
 
 

@@ -111,3 +111,73 @@ def test_empty_class_list_matches_nothing():
     pred[..., :4] *= 300
     assert all(d.shape == (0, 6) for d in R.non_max_suppression(pred, 0.25, 0.45, classes=[]))
     assert any(d.shape[0] > 0 for d in R.non_max_suppression(pred, 0.25, 0.45, classes=None))
+
+
+# ---- fused decode + confidence filter (ry_decode_filter / ry_nms_filtered, north_star (c)) ----
+def _host_mask(pred, conf):
+    """The candidate mask the Detect epilogue would leave for `pred`: bit (i & 31) of word (i >> 5) = pred[b, i, 4] > conf."""
+    B, N, _ = pred.shape
+    words = (N + 31) // 32
+    xc = (pred[..., 4] > np.float32(conf)).cpu().numpy()
+    bits = np.zeros((B, words * 32), dtype=np.uint8)
+    bits[:, :N] = xc
+    packed = np.packbits(bits.reshape(B, words, 32), axis=2, bitorder='little').view(np.uint32).reshape(B, words)
+    return torch.from_numpy(packed.view(np.int32).copy())
+
+
+def _with_mask(pred, conf, mask_conf=None):
+    pred = pred.cuda().contiguous()
+    pred._ry_cand = (_host_mask(pred, conf if mask_conf is None else mask_conf).cuda(), float(conf if mask_conf is None else mask_conf),
+                     pred.data_ptr())
+    return pred
+
+
+def test_filtered_front_end_matches_plain_on_every_case():
+    """ry_nms_filtered (ordered compaction from the mask words) == ry_nms (every row tested): same bytes on the reference-minted
+    golden cases and on the synthetic / multi-label / class-filter / agnostic / > max_nms cases above."""
+    import repyolo_b200 as R
+    g = np.load(os.path.join(GOLDEN, 'nms_cases.npz'))
+    meta = json.loads(bytes(g['meta']).decode())
+    for name, kw in meta.items():
+        pred = torch.from_numpy(g[f'{name}.pred'])
+        conf = kw.get('conf_thres', 0.25)
+        outs = R.non_max_suppression(_with_mask(pred, conf), **kw)
+        got = torch.cat(outs, 0).cpu().numpy()
+        assert [o.shape[0] for o in outs] == g[f'{name}.counts'].tolist(), name
+        assert got.tobytes() == g[f'{name}.out'].tobytes(), name
+    for N, nc, conf, iou, kw in [(25200, 1, 0.25, 0.45, {}), (25200, 1, 0.001, 0.65, dict(multi_label=True)),
+                                 (6000, 4, 0.1, 0.6, dict(multi_label=True)), (6000, 4, 0.25, 0.45, dict(classes=[1, 3])),
+                                 (3000, 4, 0.25, 0.45, dict(agnostic=True)), (4000, 20, 0.001, 0.65, dict(multi_label=True)),
+                                 (37, 1, 0.25, 0.45, {}), (1, 1, 0.25, 0.45, {})]:
+        pred = _synthetic(3, N, nc, seed=7 * N + nc, tie=(N == 6000))
+        pred[1, :, 4] *= 0.0 if N == 3000 else 1.0
+        plain = R.non_max_suppression(pred.cuda(), conf, iou, **kw)
+        _same(R.non_max_suppression(_with_mask(pred, conf), conf, iou, **kw), plain, ('filtered', N, nc, conf))
+        # a mask made with a LOWER threshold is a superset: still exact
+        _same(R.non_max_suppression(_with_mask(pred, conf, mask_conf=conf * 0.5), conf, iou, **kw), plain, ('superset', N, nc, conf))
+
+
+@pytest.mark.parametrize('B,H,W,nc,conf', [(2, 640, 640, 1, 0.25), (3, 96, 160, 1, 0.001), (5, 64, 64, 1, 0.25), (2, 128, 96, 2, 0.1),
+                                           (64, 640, 640, 1, 0.25)])
+def test_decode_filter_mask_and_detections(B, H, W, nc, conf):
+    """Model.decode_filter: same pred as the plain forward, mask == (pred[..., 4] > conf) bit for bit (image boundaries inside
+    a warp at the small maps, generic head nc = 2, BASELINE batch 64), detections byte-identical to pred -> ry_nms."""
+    import repyolo_b200 as R
+    from oracle import repyolo_oracle as O
+    layers, save, sd, fz = O.make_model(seed=0, mode='calibrated', nc=nc)
+    m = R.Model(nc=nc)
+    m.load_state_dict(sd, strict=True)
+    m.fuse()
+    x = torch.rand(B, 3, H, W, generator=torch.Generator().manual_seed(B * H + W)).cuda()
+    plain, _ = m(x)
+    assert not hasattr(plain, '_ry_cand')
+    m.decode_filter = conf
+    pred, _ = m(x)
+    m.decode_filter = None
+    assert torch.equal(pred, plain)
+    mask, mconf, ptr = pred._ry_cand
+    assert mconf == conf and ptr == pred.data_ptr()
+    assert torch.equal(mask.cpu(), _host_mask(pred, conf))
+    assert int((pred[..., 4] > conf).sum()) > 0
+    for c2, iou in ((conf, 0.45), (max(conf, 0.3), 0.65)):
+        _same(R.non_max_suppression(pred, c2, iou), R.non_max_suppression(plain, c2, iou), ('decode_filter', B, H, W, nc, c2))

@@ -21,7 +21,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     lib = ctypes.CDLL(so)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.ry_abi_version() == 4
+    assert lib.ry_abi_version() == 5
     N = importlib.import_module('rep-yolo_b200._lib')
     assert sorted(N.EXPORTS) == declared               # the ctypes binding covers the whole header
     assert lib.ry_abi_sizeof(1) == ctypes.sizeof(N.OpDesc) and lib.ry_abi_sizeof(0) == ctypes.sizeof(N.TensorDesc)
