@@ -177,6 +177,7 @@ def workload_config(args):
     return {'workload': f'Rep-YOLO fused, batch {args.batch} per GPU at {args.size}x{args.size}, Detect decode + NMS '
                         f'(conf {CONF}, iou {IOU}) in-loop; weights: synthetic {args.init} init (seed 0)',
             'batch_per_gpu': args.batch, 'img_size': args.size, 'conf_thres': CONF, 'iou_thres': IOU,
+            'decode_filter': not getattr(args, 'no_decode_filter', False),
             'l2_policy': 'inputs larger than L2 (fp32 image batch = %.0f MB, uint8 batch = %.0f MB; activations 5 GB per step)' % (
                 args.batch * 3 * args.size * args.size * 4 / 1e6, args.batch * 3 * args.size * args.size / 1e6),
             'parallelism': f'batch-sharded dp{args.gpus}, NCCL all-gather of [B,300,6] detections' if args.gpus > 1 else 'single GPU'}
@@ -227,6 +228,8 @@ def run_native(args):
     model = R.Model()
     model.load_state_dict(sd, strict=True)
     model.fuse()
+    # fused decode + confidence filter (ry_decode_filter -> ry_nms_filtered): same pred, byte-identical detections
+    model.decode_filter = None if args.no_decode_filter else CONF
     g = torch.Generator().manual_seed(1000 + rank)
     n_bufs = 2
     # e2e ships uint8 NCHW images to the device exactly like the reference's detect.py:73-78 (torch.from_numpy(img).to(device),
@@ -376,6 +379,11 @@ def run_native(args):
                 'frac_of_hbm_peak': by / (t * 1e-3) / 1e9 / peaks()['hbm']}
     pred_main, _ = model(xdev[0])
     nms_legs = {args.init: nms_leg(pred_main)}
+    if hasattr(pred_main, '_ry_cand'):                 # the same candidates through the plain front end (every row of pred tested)
+        plain = pred_main.clone()
+        nms_legs[args.init]['plain_front_end_ms_per_step'] = nms_leg(plain)['ms_per_step']
+        nms_legs[args.init]['front_end'] = 'ry_decode_filter mask -> ry_nms_filtered'
+        del plain
     other = 'default' if args.init != 'default' else 'calibrated'
     if rank == 0 and not args.no_nms_legs:
         _, _, sd2, _ = O.make_model(seed=0, mode=other)
@@ -530,6 +538,7 @@ def main():
                          "'calibrated' = SURVEY App. D statistics-calibrated init (realistic candidate counts)")
     ap.add_argument('--ref-sample', type=int, default=4, help='images per step of the CPU reference arm / cpu_baseline')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-decode-filter', action='store_true', help='plain front end: ry_forward -> ry_nms tests every row of pred')
     ap.add_argument('--no-nms-legs', action='store_true', help='skip the second-init NMS leg (A/B runs)')
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == 'native':

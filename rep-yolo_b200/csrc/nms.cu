@@ -1,12 +1,13 @@
 // non_max_suppression on the GPU, bit-exact against the reference (utils/general.py:953-1045 + torchvision.ops.nms).
 //
-//   1. nms_filter   : one CTA per image walks the candidates IN ORDER: obj > conf (fp32), conf = obj*cls (nc > 1) or obj
-//                     (nc == 1, general.py:994-998), xywh->xyxy (general.py:265-272, same op order), best-class or
-//                     multi-label rows, class filter; ordered (prefix-sum) compaction -> rows[n][6] + sort keys.
+//   1. nms_compact  : one CTA per image: obj > conf (fp32), conf = obj*cls (nc > 1) or obj (nc == 1, general.py:994-998),
+//                     xywh->xyxy (general.py:265-272, same op order), best-class or multi-label rows, class filter;
+//                     ordered (prefix-sum) compaction -> rows[n][6] + sort keys.  <true>: driven by the `obj > conf`
+//                     ballot words the Detect epilogue left (ry_decode_filter): only the rows that passed are read.
 //   2. radix sort   : stable LSD radix sort (4 x 8 bit) of the keys per image, score descending; stability gives the
 //                     "ties -> lower index first" order of torchvision's stable sort.  hist -> scan -> scatter per pass.
-//   3. nms_scan     : one CTA per image consumes the sorted candidates in chunks of 512: suppress by the boxes kept so
-//                     far, build the 512x512 bit mask of the chunk (class-offset boxes, general.py:1027-1028), resolve
+//   3. nms_scan     : one CTA per image consumes the sorted candidates in steps of 128: suppress by the boxes kept so
+//                     far, build the 128x128 bit mask of the survivors (class-offset boxes, general.py:1027-1028), resolve
 //                     it with a deterministic serial keep-scan, stop at max_det keeps (exact: general.py:1030-1031
 //                     truncates AFTER nms and greedy decisions only depend on higher-ranked boxes) or after max_nms
 //                     candidates (general.py:1023-1024, stable variant).
@@ -27,8 +28,6 @@ constexpr int kSortThreads = 256;
 constexpr int kSortWarps = kSortThreads / 32;
 constexpr int kSortItems = 16;                           // keys per thread
 constexpr int kSortTile = kSortThreads * kSortItems;     // 4096 keys per CTA
-constexpr int kChunk = 512;                              // sorted candidates per scan step
-constexpr int kChunkWords = kChunk / 64;
 constexpr float kMaxWh = 4096.0f;                        // general.py:965
 
 __device__ __forceinline__ uint32_t desc_key(float s) {
@@ -138,67 +137,87 @@ __device__ __forceinline__ int cand_emit(const float *__restrict__ p, const Cand
     return off;
 }
 
-// front end 1: every row of pred is read and tested, one candidate per thread per trip, ordered (prefix-sum) compaction
-__global__ void __launch_bounds__(kFilterThreads) nms_filter_kernel(const float *__restrict__ pred, int N, int nc,
-                                                                    float conf, int multi_label,
-                                                                    const int *__restrict__ classes, int n_classes,
-                                                                    size_t cap, float *__restrict__ rows,
-                                                                    uint32_t *__restrict__ keys, uint32_t *__restrict__ idx,
-                                                                    int *__restrict__ counts) {
-    __shared__ int warp_sums[32];
-    const int b = blockIdx.x, no = 5 + nc;
-    const float *P = pred + (size_t)b * N * no;
-    float *R = rows + (size_t)b * cap * 6;
-    uint32_t *Kb = keys + (size_t)b * cap, *Ib = idx + (size_t)b * cap;
-    int base = 0;
-    for (int i0 = 0; i0 < N; i0 += blockDim.x) {
-        const int i = i0 + threadIdx.x;
-        const float *p = P + (size_t)i * no;
-        Cand c;
-        const int cnt = i < N ? cand_eval(p, nc, conf, multi_label, classes, n_classes, c) : 0;
-        int total;
-        const int off = base + block_excl_scan(cnt, warp_sums, &total);
-        if (cnt > 0) cand_emit(p, c, nc, conf, multi_label, classes, n_classes, R, Kb, Ib, off);
-        base += total;
-    }
-    if (threadIdx.x == 0) counts[b] = base;
-}
-
-// front end 2 (fused decode + filter, ry_decode_filter): the Detect epilogue already evaluated `obj > conf` for every
-// candidate it decoded and left the result as ballot words mask[b][ceil(N / 32)] (bit i & 31 of word i >> 5).  One thread
-// per mask word walks its set bits in index order; the block-wide prefix sum over the words' row counts gives the same
-// ordered compaction as front end 1, but only the rows that passed are ever read.
-__global__ void __launch_bounds__(kFilterThreads) nms_gather_kernel(const float *__restrict__ pred, const uint32_t *__restrict__ mask,
-                                                                    int N, int nc, float conf, int multi_label,
-                                                                    const int *__restrict__ classes, int n_classes, size_t cap,
-                                                                    float *__restrict__ rows, uint32_t *__restrict__ keys,
-                                                                    uint32_t *__restrict__ idx, int *__restrict__ counts) {
+// Ordered compaction, one CTA per image.  Work unit = one warp x 32 consecutive candidates (a "word"):
+//   phase 1  every warp walks its words (stride = warps per CTA, no block barrier inside): lane l evaluates candidate 32w + l,
+//            the warp's row count and the ballot of the passing lanes go to shared memory;
+//   phase 2  ONE block-wide exclusive scan over the per-word counts (ordered, deterministic: no atomics);
+//   phase 3  the warps revisit their words, only the passing lanes re-read their row, and write rows / sort keys at
+//            word offset + intra-warp prefix.
+// MASKED = false (ry_nms): every row of pred is read and tested.  MASKED = true (ry_nms_filtered): the Detect epilogue
+// already evaluated `obj > conf` for every candidate it decoded and left the result as ballot words
+// mask[b][ceil(N / 32)] (ry_decode_filter); rows whose bit is clear are never read.
+template <bool MASKED>
+__global__ void __launch_bounds__(kFilterThreads) nms_compact_kernel(const float *__restrict__ pred, const uint32_t *__restrict__ mask,
+                                                                     int N, int nc, float conf, int multi_label,
+                                                                     const int *__restrict__ classes, int n_classes, size_t cap,
+                                                                     float *__restrict__ rows, uint32_t *__restrict__ keys,
+                                                                     uint32_t *__restrict__ idx, int *__restrict__ counts) {
+    extern __shared__ int sm_words[];                     // [words] row count -> exclusive offset | [words] ballot of passing lanes
     __shared__ int warp_sums[32];
     const int b = blockIdx.x, no = 5 + nc, words = (N + 31) >> 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    int *wcnt = sm_words;
+    uint32_t *wpass = reinterpret_cast<uint32_t *>(sm_words + words);
     const float *P = pred + (size_t)b * N * no;
-    const uint32_t *M = mask + (size_t)b * words;
+    const uint32_t *M = MASKED ? mask + (size_t)b * words : nullptr;
     float *R = rows + (size_t)b * cap * 6;
     uint32_t *Kb = keys + (size_t)b * cap, *Ib = idx + (size_t)b * cap;
+    // kU words per trip: the objectness loads of all of them are in flight before the first test (a warp walks ~25 words of a
+    // 25200-candidate image; one dependent load per trip made this phase pure memory latency)
+    constexpr int kU = 4;
+    for (int w0 = warp; w0 < words; w0 += kU * nwarps) {
+        float obj[kU];
+        uint32_t bits[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const int w = w0 + u * nwarps, i = 32 * w + lane;
+            bits[u] = w < words ? (MASKED ? M[w] : 0xffffffffu) : 0u;
+            obj[u] = (i < N && ((bits[u] >> lane) & 1u)) ? P[(size_t)i * no + 4] : -INFINITY;
+        }
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const int w = w0 + u * nwarps, i = 32 * w + lane;
+            if (w >= words) break;
+            Cand c;
+            int cnt = 0;
+            if (obj[u] > conf) cnt = cand_eval(P + (size_t)i * no, nc, conf, multi_label, classes, n_classes, c);
+            const uint32_t pm = __ballot_sync(0xffffffffu, cnt > 0);
+            const int tot = multi_label ? __reduce_add_sync(0xffffffffu, cnt) : __popc(pm);
+            if (lane == 0) { wcnt[w] = tot; wpass[w] = pm; }
+        }
+    }
+    __syncthreads();
     int base = 0;
     for (int w0 = 0; w0 < words; w0 += blockDim.x) {
         const int w = w0 + threadIdx.x;
-        const uint32_t bits = w < words ? M[w] : 0u;
-        int cnt = 0;
-        Cand c;
-        for (uint32_t m = bits; m; m &= m - 1) {
-            const int i = 32 * w + __ffs(m) - 1;
-            if (i < N) cnt += cand_eval(P + (size_t)i * no, nc, conf, multi_label, classes, n_classes, c);
-        }
+        const int v = w < words ? wcnt[w] : 0;
         int total;
-        int off = base + block_excl_scan(cnt, warp_sums, &total);
-        for (uint32_t m = bits; m && cnt > 0; m &= m - 1) {
-            const int i = 32 * w + __ffs(m) - 1;
-            if (i >= N) break;
-            const float *p = P + (size_t)i * no;
-            if (cand_eval(p, nc, conf, multi_label, classes, n_classes, c) > 0)
-                off = cand_emit(p, c, nc, conf, multi_label, classes, n_classes, R, Kb, Ib, off);
-        }
+        const int ex = block_excl_scan(v, warp_sums, &total);
+        if (w < words) wcnt[w] = base + ex;
         base += total;
+    }
+    __syncthreads();
+    for (int w = warp; w < words; w += nwarps) {
+        const uint32_t pm = wpass[w];
+        if (!pm) continue;
+        const int i = 32 * w + lane;
+        const float *p = P + (size_t)i * no;
+        Cand c;
+        int cnt = 0;
+        if ((pm >> lane) & 1u) cnt = cand_eval(p, nc, conf, multi_label, classes, n_classes, c);
+        int pre;
+        if (multi_label) {                               // rows per candidate vary: shuffle scan
+            int x = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, x, o);
+                if (lane >= o) x += y;
+            }
+            pre = x - cnt;
+        } else {
+            pre = __popc(pm & ((1u << lane) - 1u));
+        }
+        if (cnt > 0) cand_emit(p, c, nc, conf, multi_label, classes, n_classes, R, Kb, Ib, wcnt[w] + pre);
     }
     if (threadIdx.x == 0) counts[b] = base;
 }
@@ -391,64 +410,98 @@ __device__ __forceinline__ bool iou_gt(float ax1, float ay1, float ax2, float ay
     return ovr >= thr.t_up;
 }
 
-__global__ void __launch_bounds__(kChunk) nms_scan_kernel(const float *__restrict__ rows, const uint32_t *__restrict__ order,
-                                                          const int *__restrict__ counts, size_t cap, IouThr iou_thr,
-                                                          int agnostic, int max_det, int max_nms, float *__restrict__ out,
-                                                          int *__restrict__ out_counts) {
-    extern __shared__ unsigned char smraw[];
-    // survivor boxes of the chunk (SoA) | mask | kept boxes (SoA) | control
-    float *cx1 = reinterpret_cast<float *>(smraw), *cy1 = cx1 + kChunk, *cx2 = cy1 + kChunk, *cy2 = cx2 + kChunk, *car = cy2 + kChunk;
-    unsigned long long *mask = reinterpret_cast<unsigned long long *>(car + kChunk);       // [survivors][words]
-    const int kcap = (max_det + 3) & ~3;                                                     // kept list padded to the unroll of the check loop
-    float4 *kbox = reinterpret_cast<float4 *>(mask + (size_t)kChunk * kChunkWords);          // [kcap] (x1, y1, x2, y2) with class offset
-    float *kar = reinterpret_cast<float *>(kbox + kcap);                                     // [kcap] areas
-    int *ctl = reinterpret_cast<int *>(kar + kcap);                                          // [0] kept so far, [1] new keeps of the chunk
-    int *newkeep = ctl + 2;                                                                  // [kChunk] survivor indices kept
-    int *sidx = newkeep + kChunk;                                                            // [kChunk] survivor -> position in the chunk
-    int *wcnt = sidx + kChunk;                                                               // [kChunk / 32] survivors per warp
+// One CTA per image, steps of kCh = 128 sorted candidates (the 512-candidate step spent its time in a 512 x 512
+// pair mask and a ~100-cycle-per-keep warp scan on ONE SM per image, although max_det = 300 keeps are usually found within
+// the first few hundred candidates).  Per step:
+//   1. kept-list test: kSub = 4 threads per candidate share the (<= max_det) kept boxes, 4 independent IoUs per trip each;
+//   2. ballot-compaction of the survivors (order preserved);
+//   3. survivor x survivor mask, one 32-bit word per thread (128 x 4 words);
+//   4. keep-scan by ONE thread with the 128 dead bits in four registers: per keep one 16-byte shared-memory row read;
+//   5. publish the new keeps (kept-box list + output rows).
+// The rows of the NEXT step are fetched (sort order -> row gather, two dependent loads) while the current step runs.
+constexpr int kScanThreads = 512;
+constexpr int kCh = 128;
+constexpr int kSub = kScanThreads / kCh;
+
+__global__ void __launch_bounds__(kScanThreads) nms_scan_kernel(const float *__restrict__ rows, const uint32_t *__restrict__ order,
+                                                                const int *__restrict__ counts, size_t cap, IouThr iou_thr,
+                                                                int agnostic, int max_det, int max_nms, float *__restrict__ out,
+                                                                int *__restrict__ out_counts) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    // survivor mask rows (16 B each) | kept boxes | survivor boxes of the step (SoA) | kept areas | control
+    uint4 *mask = reinterpret_cast<uint4 *>(smraw);                                          // [kCh] bit j of row i: i suppresses j (j > i)
+    const int kcap = (max_det + 3) & ~3;                                                     // kept list padded to the unroll of the test loop
+    float4 *kbox = reinterpret_cast<float4 *>(mask + kCh);                                   // [kcap] (x1, y1, x2, y2) with class offset
+    float *cx1 = reinterpret_cast<float *>(kbox + kcap), *cy1 = cx1 + kCh, *cx2 = cy1 + kCh, *cy2 = cx2 + kCh, *car = cy2 + kCh;
+    float *kar = car + kCh;                                                                  // [kcap] areas
+    int *ctl = reinterpret_cast<int *>(kar + kcap);                                          // [0] kept so far, [1] new keeps of the step
+    int *newkeep = ctl + 2;                                                                  // [kCh] survivor indices kept
+    float *srow = reinterpret_cast<float *>(newkeep + kCh);                                  // [kCh][6] survivor rows as they go out
+    int *wcnt = reinterpret_cast<int *>(srow + kCh * 6);                                     // [kScanThreads / 32] survivors per warp
 
     const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int cand = tid / kSub, sub = tid - cand * kSub;
     const int n = min(counts[b], max_nms);
     const float *R = rows + (size_t)b * cap * 6;
     const uint32_t *O = order + (size_t)b * cap;
     float *outb = out + (size_t)b * max_det * 6;
     if (tid == 0) { ctl[0] = 0; ctl[1] = 0; }
-    for (int k = tid; k < kcap; k += kChunk) {                   // padding entries never intersect anything (inter == 0 -> not suppressed)
+    for (int k = tid; k < kcap; k += kScanThreads) {             // padding entries never intersect anything (inter == 0 -> not suppressed)
         kbox[k] = make_float4(3.0e38f, 3.0e38f, 3.0e38f, 3.0e38f);
         kar[k] = 0.0f;
     }
+    // rows of the first step (the leader lane of each candidate loads, its kSub - 1 siblings get the box by shuffle)
+    float nr0 = 0, nr1 = 0, nr2 = 0, nr3 = 0, nr4 = 0, nr5 = 0;
+    if (sub == 0 && cand < n) {
+        const float *r = R + (size_t)O[cand] * 6;
+        nr0 = r[0]; nr1 = r[1]; nr2 = r[2]; nr3 = r[3]; nr4 = r[4]; nr5 = r[5];
+    }
     __syncthreads();
 
-    for (int c0 = 0; c0 < n; c0 += kChunk) {
-        const int cs = min(kChunk, n - c0);
+    for (int c0 = 0; c0 < n; c0 += kCh) {
+        const int cs = min(kCh, n - c0);
         const int kept0 = ctl[0];
         if (kept0 >= max_det) break;
+        const float r0 = nr0, r1 = nr1, r2 = nr2, r3 = nr3, r4 = nr4, r5 = nr5;
+        if (sub == 0 && c0 + kCh + cand < n) {                   // next step's rows: in flight during this step
+            const float *r = R + (size_t)O[c0 + kCh + cand] * 6;
+            nr0 = r[0]; nr1 = r[1]; nr2 = r[2]; nr3 = r[3]; nr4 = r[4]; nr5 = r[5];
+        }
         // ---- my box (class offset added in fp32 BEFORE the IoU, general.py:1027-1028); suppressed by an earlier keep? ----
-        bool alive = false;
         float x1 = 0, y1 = 0, x2 = 0, y2 = 0, ar = 0;
-        if (tid < cs) {
-            const float *r = R + (size_t)O[c0 + tid] * 6;
-            const float off = agnostic ? __fmul_rn(r[5], 0.0f) : __fmul_rn(r[5], kMaxWh);
-            x1 = __fadd_rn(r[0], off); y1 = __fadd_rn(r[1], off); x2 = __fadd_rn(r[2], off); y2 = __fadd_rn(r[3], off);
+        if (sub == 0) {
+            const float off = agnostic ? __fmul_rn(r5, 0.0f) : __fmul_rn(r5, kMaxWh);
+            x1 = __fadd_rn(r0, off); y1 = __fadd_rn(r1, off); x2 = __fadd_rn(r2, off); y2 = __fadd_rn(r3, off);
             ar = __fmul_rn(__fsub_rn(x2, x1), __fsub_rn(y2, y1));
-            alive = true;
-            for (int k = 0; k < kept0; k += 4) {                 // four independent tests per trip (the loop is latency bound)
-                bool sup = false;
+        }
+        const int src = lane & ~(kSub - 1);
+        x1 = __shfl_sync(0xffffffffu, x1, src); y1 = __shfl_sync(0xffffffffu, y1, src);
+        x2 = __shfl_sync(0xffffffffu, x2, src); y2 = __shfl_sync(0xffffffffu, y2, src);
+        ar = __shfl_sync(0xffffffffu, ar, src);
+        bool sup = false;
+        if (cand < cs) {
+            for (int k = 4 * sub; k < kept0 && !sup; k += 4 * kSub) {          // four independent tests per trip (the loop is latency bound)
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const float4 kb = kbox[k + u];
                     sup |= (k + u < kept0) & iou_gt(kb.x, kb.y, kb.z, kb.w, kar[k + u], x1, y1, x2, y2, ar, iou_thr);
                 }
-                if (sup) { alive = false; break; }
             }
         }
+        {
+            int s = sup ? 1 : 0;
+#pragma unroll
+            for (int o = 1; o < kSub; o <<= 1) s |= __shfl_xor_sync(0xffffffffu, s, o);
+            sup = s != 0;
+        }
+        const bool alive = sub == 0 && cand < cs && !sup;
         // ---- compact the survivors (order preserved): only they can be kept or suppress anything from here on ----
         const uint32_t am = __ballot_sync(0xffffffffu, alive);
         if (lane == 0) wcnt[warp] = __popc(am);
         __syncthreads();
         int base = 0, S = 0;
 #pragma unroll
-        for (int w = 0; w < kChunk / 32; ++w) {
+        for (int w = 0; w < kScanThreads / 32; ++w) {
             const int c = wcnt[w];
             if (w < warp) base += c;
             S += c;
@@ -456,54 +509,55 @@ __global__ void __launch_bounds__(kChunk) nms_scan_kernel(const float *__restric
         if (alive) {
             const int ci = base + __popc(am & ((1u << lane) - 1));
             cx1[ci] = x1; cy1[ci] = y1; cx2[ci] = x2; cy2[ci] = y2; car[ci] = ar;
-            sidx[ci] = tid;
+            float *o = srow + ci * 6;                            // the row as it goes out (un-offset box, general.py:1040)
+            o[0] = r0; o[1] = r1; o[2] = r2; o[3] = r3; o[4] = r4; o[5] = r5;
         }
         __syncthreads();
-        const int words = (S + 63) >> 6;
-        // ---- survivor mask: mask[i][w] bit j = survivor i suppresses survivor (64w + j), only j > i matters ----
-        // (work item = (word w, survivor i) with i fastest: the lanes of a warp test the SAME box j against their own box i, so
-        //  the shared-memory reads of j are broadcasts instead of an 8-way bank conflict between words)
-        for (int e = tid; e < S * words; e += kChunk) {
-            const int w = e / S, r = e - w * S;
-            const int i = (w & 1) ? S - 1 - r : r;            // alternate directions: a thread's rows of the triangle add up evenly
-            unsigned long long bits = 0;
-            if (64 * w + 63 > i) {
+        // ---- survivor mask: thread (i = tid / 4, w = tid % 4) -> bits j = 32w .. 32w+31 (only j > i matters) of row i ----
+        {
+            const int i = tid >> 2, w = tid & 3;
+            uint32_t bits = 0;
+            if (i < S && 32 * w + 31 > i) {
                 const float ax1 = cx1[i], ay1 = cy1[i], ax2 = cx2[i], ay2 = cy2[i], aa = car[i];
-                const int j0 = max(64 * w, i + 1), j1 = min(64 * w + 64, S);
+                const int j0 = max(32 * w, i + 1), j1 = min(32 * w + 32, S);
                 for (int j = j0; j < j1; ++j)
-                    if (iou_gt(ax1, ay1, ax2, ay2, aa, cx1[j], cy1[j], cx2[j], cy2[j], car[j], iou_thr)) bits |= 1ull << (j & 63);
+                    if (iou_gt(ax1, ay1, ax2, ay2, aa, cx1[j], cy1[j], cx2[j], cy2[j], car[j], iou_thr)) bits |= 1u << (j & 31);
             }
-            mask[(size_t)i * words + w] = bits;
+            reinterpret_cast<uint32_t *>(mask)[tid] = bits;
         }
         __syncthreads();
-        // ---- deterministic keep-scan by one warp: lane l owns 32-bit word l of the dead set (S <= 512: 16 words); one step =
-        //      local find-first-set, a warp min-reduction, one broadcast row read; <= S steps, early exit at max_det ----
-        if (warp == 0) {
-            const uint32_t *mask32 = reinterpret_cast<const uint32_t *>(mask);
-            const int w32 = 2 * words;
-            uint32_t myd = 0xffffffffu;
-            if (lane < w32) myd = (32 * lane + 32 <= S) ? 0u : (32 * lane >= S ? 0xffffffffu : ~((1u << (S - 32 * lane)) - 1u));
+        // ---- deterministic keep-scan, one thread, dead set in registers ----
+        if (tid == 0) {
+            uint32_t d0, d1, d2, d3;
+            {
+                auto tail = [&](int wbase) -> uint32_t { return S >= wbase + 32 ? 0u : (S <= wbase ? 0xffffffffu : ~((1u << (S - wbase)) - 1u)); };
+                d0 = tail(0); d1 = tail(32); d2 = tail(64); d3 = tail(96);
+            }
             int kept = kept0, nk = 0;
-            while (kept < max_det) {
-                const uint32_t al = ~myd;
-                const uint32_t cand = al ? (uint32_t)(32 * lane + __ffs(al) - 1) : 0x7fffffffu;
-                const uint32_t i = __reduce_min_sync(0xffffffffu, cand);
-                if (i == 0x7fffffffu) break;
-                if (lane == 0) newkeep[nk] = (int)i;
-                ++nk; ++kept;
-                uint32_t m = lane < w32 ? mask32[(size_t)i * w32 + lane] : 0u;
-                if (lane == (int)(i >> 5)) m |= 1u << (i & 31);    // consumed
-                myd |= m;
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                while (kept < max_det) {
+                    const uint32_t dw = w == 0 ? d0 : (w == 1 ? d1 : (w == 2 ? d2 : d3));
+                    const uint32_t al = ~dw;
+                    if (!al) break;
+                    const int bit = __ffs(al) - 1, i = 32 * w + bit;
+                    newkeep[nk++] = i;
+                    ++kept;
+                    const uint4 m = mask[i];
+                    d0 |= m.x; d1 |= m.y; d2 |= m.z; d3 |= m.w;
+                    if (w == 0) d0 |= 1u << bit; else if (w == 1) d1 |= 1u << bit; else if (w == 2) d2 |= 1u << bit; else d3 |= 1u << bit;   // consumed
+                }
             }
-            if (lane == 0) { ctl[0] = kept; ctl[1] = nk; }
+            ctl[0] = kept;
+            ctl[1] = nk;
         }
         __syncthreads();
-        // ---- publish the new keeps: kept-box list (for later chunks) and output rows (un-offset boxes, general.py:1040) ----
+        // ---- publish the new keeps: kept-box list (for later steps) and output rows (un-offset boxes, general.py:1040) ----
         const int nk = ctl[1];
-        for (int t = tid; t < nk; t += kChunk) {
+        for (int t = tid; t < nk; t += kScanThreads) {
             const int i = newkeep[t], slot = kept0 + t;
             kbox[slot] = make_float4(cx1[i], cy1[i], cx2[i], cy2[i]); kar[slot] = car[i];
-            const float *r = R + (size_t)O[c0 + sidx[i]] * 6;
+            const float *r = srow + i * 6;
             float *o = outb + (size_t)slot * 6;
 #pragma unroll
             for (int q = 0; q < 6; ++q) o[q] = r[q];
@@ -565,10 +619,15 @@ int nms_run(const float *pred, const uint32_t *cand_mask, int B, int N, int nc, 
     int *cls = reinterpret_cast<int *>(ws + L.classes);
     if (n_classes > 0) RY_CUDA(cudaMemcpyAsync(cls, classes_host, (size_t)n_classes * 4, cudaMemcpyHostToDevice, st));
 
-    if (cand_mask != nullptr)
-        nms_gather_kernel<<<B, kFilterThreads, 0, st>>>(pred, cand_mask, N, nc, conf, multi_label, cls, n_classes, L.cap, rows, k0, i0, cnt);
-    else
-        nms_filter_kernel<<<B, kFilterThreads, 0, st>>>(pred, N, nc, conf, multi_label, cls, n_classes, L.cap, rows, k0, i0, cnt);
+    const size_t csm = (size_t)((N + 31) / 32) * 8;
+    if (csm > 200 * 1024) RY_FAIL("ry_nms: more than 800k candidates per image");
+    if (cand_mask != nullptr) {
+        RY_CUDA(RY_ENSURE_DYN_SMEM(nms_compact_kernel<true>, 200 * 1024));
+        nms_compact_kernel<true><<<B, kFilterThreads, csm, st>>>(pred, cand_mask, N, nc, conf, multi_label, cls, n_classes, L.cap, rows, k0, i0, cnt);
+    } else {
+        RY_CUDA(RY_ENSURE_DYN_SMEM(nms_compact_kernel<false>, 200 * 1024));
+        nms_compact_kernel<false><<<B, kFilterThreads, csm, st>>>(pred, nullptr, N, nc, conf, multi_label, cls, n_classes, L.cap, rows, k0, i0, cnt);
+    }
     static const bool no_solo = getenv("RY_NMS_MULTI_SORT") != nullptr;
     const bool solo = !no_solo && L.cap <= (size_t)kSoloMaxCap;
     if (solo) sort_image_kernel<<<B, kSoloThreads, 0, st>>>(k0, i0, k1, i1, cnt, L.cap);      // four passes: the result is back in k0 / i0
@@ -581,8 +640,8 @@ int nms_run(const float *pred, const uint32_t *cand_mask, int B, int N, int nc, 
         uint32_t *t = k0; k0 = k1; k1 = t;
         t = i0; i0 = i1; i1 = t;
     }
-    const size_t smem = (size_t)5 * kChunk * 4 + (size_t)kChunk * kChunkWords * 8 + (size_t)5 * ((max_det + 3) & ~3) * 4 + 2 * 4 +
-                        (size_t)2 * kChunk * 4 + (kChunk / 32) * 4;
+    const size_t smem = (size_t)kCh * 16 + (size_t)5 * ((max_det + 3) & ~3) * 4 + (size_t)5 * kCh * 4 + 2 * 4 + (size_t)7 * kCh * 4 +
+                        (kScanThreads / 32) * 4;
     RY_CUDA(RY_ENSURE_DYN_SMEM(nms_scan_kernel, 200 * 1024));
     IouThr thr;
     {   // smallest float strictly greater than the double threshold
@@ -592,7 +651,7 @@ int nms_run(const float *pred, const uint32_t *cand_mask, int B, int N, int nc, 
         thr.t_up = tf;
         thr.nonneg = iou >= 0.0 ? 1 : 0;
     }
-    nms_scan_kernel<<<B, kChunk, smem, st>>>(rows, i0, cnt, L.cap, thr, agnostic, max_det, max_nms, out, counts);
+    nms_scan_kernel<<<B, kScanThreads, smem, st>>>(rows, i0, cnt, L.cap, thr, agnostic, max_det, max_nms, out, counts);
     RY_CUDA(cudaGetLastError());
     return 0;
 }
