@@ -49,10 +49,29 @@ def greedy_nms(boxes, scores, iou_thres: float, max_keep: int | None = None) -> 
     return keep[:k].astype(np.int64)
 
 
+def with_apriori_labels(prediction, labels):
+    """general.py:981-987: per image the label rows (cls, x, y, w, h) become candidates [box, conf = 1, one-hot class] appended
+    BEHIND the rows that pass the confidence filter.  Restated as a dense tensor: Lmax extra rows per image behind the N
+    candidates; unused rows carry obj = -inf, which never passes `obj > conf_thres`."""
+    if labels is None or not len(labels) or not any(len(l) for l in labels):
+        return prediction
+    B, n, no = prediction.shape
+    lmax = max(len(l) for l in labels)
+    extra = torch.zeros((B, lmax, no), dtype=prediction.dtype)
+    extra[:, :, 4] = float('-inf')
+    for b, l in enumerate(labels):
+        l = torch.as_tensor(l, dtype=torch.float32).reshape(-1, 5)
+        if len(l):
+            extra[b, :len(l), :4] = l[:, 1:5]
+            extra[b, :len(l), 4] = 1.0
+            extra[b, torch.arange(len(l)), l[:, 0].long() + 5] = 1.0
+    return torch.cat([prediction, extra], 1)
+
+
 def non_max_suppression(prediction, conf_thres=0.25, iou_thres=0.45, classes=None, agnostic=False, multi_label=False,
                         labels=(), max_det=300, max_nms=30000):
-    assert not labels, 'apriori labels (save_hybrid) are outside the hot path'
-    p = np.ascontiguousarray(prediction.detach().cpu().numpy().astype(np.float32, copy=False))
+    prediction = with_apriori_labels(prediction.detach().cpu().float(), labels)
+    p = np.ascontiguousarray(prediction.numpy().astype(np.float32, copy=False))
     B, n, no = p.shape
     out = np.zeros((B, max_det, 6), dtype=np.float32)
     counts = np.zeros(B, dtype=np.int32)

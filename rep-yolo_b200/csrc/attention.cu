@@ -110,9 +110,9 @@ struct Geom {
     size_t stats_off, e_off;    // byte offsets in the scratch region: fp32 (max, sum) of the row pass, bf16 vertical energies
 };
 
-template <bool QK, bool VV, typename Src>
+template <bool QK, bool VV, bool RAW, typename Src>
 __device__ __forceinline__ void stage_operands(const AttnW &w, int Cq, const Geom &gm, int LP, int tis, int nthr, Src src,
-                                               __nv_bfloat16 *Aq, __nv_bfloat16 *Bk, __nv_bfloat16 *Vs) {
+                                               __nv_bfloat16 *Aq, __nv_bfloat16 *Bk, __nv_bfloat16 *Vs, __nv_bfloat16 *Xr) {
     const int d = tis % Cq, r0 = tis / Cq, rstep = nthr / Cq;
     float rwq[8], rwk[8], rwv[8], rbv[8], rs1[8], rt1[8];
     float rbq = 0.0f, rbk = 0.0f, sc = 0.0f, sh = 0.0f;
@@ -144,6 +144,7 @@ __device__ __forceinline__ void stage_operands(const AttnW &w, int Cq, const Geo
             const int pi = pb + r * rstep;
             if (pi >= LP) break;
             const bool ok = pi < gm.L;
+            if (RAW) *reinterpret_cast<uint4 *>(Xr + (size_t)pi * gm.sv + d * 8) = u[r];      // the line itself, for the "+ x" of the epilogue
             const float2 f0 = unpack_bf16x2(u[r].x), f1 = unpack_bf16x2(u[r].y), f2 = unpack_bf16x2(u[r].z), f3 = unpack_bf16x2(u[r].w);
             const float xv[8] = {f0.x, f0.y, f1.x, f1.y, f2.x, f2.y, f3.x, f3.y};
             if (QK) {
@@ -241,6 +242,7 @@ __device__ __forceinline__ void store_energies(const float (&e)[NT][4], __nv_bfl
 // FUSE (column pass only): the criss-cross output column just computed is also the input column of the VerticalAttention
 // that follows (CCVA: m1(m(x)), common.py:2654-2655), whose energy pass needs exactly one image column of q/k: it runs
 // here on the column kept in shared memory (w2 = the vertical module's parameters) instead of a launch that re-reads it.
+// (forcing 5 CTAs / SM through __launch_bounds__ -- 72 registers, ~80 B of spills -- was measured slower: 0.74 vs 0.68 ms)
 template <int MODE, int NT, int LPC, bool FUSE>
 __global__ void __launch_bounds__(NT * 16 * LPC) attn_mma_kernel(const AttnParams p, const AttnW w1, const AttnW w2, const Geom gm,
                                                                  int total_lines, size_t slot_bytes) {
@@ -259,7 +261,8 @@ __global__ void __launch_bounds__(NT * 16 * LPC) attn_mma_kernel(const AttnParam
     __nv_bfloat16 *Bk = Aq + (size_t)LP * sq;
     __nv_bfloat16 *Vs = (MODE == MODE_VPV) ? Aq : Bk + (size_t)LP * sq;      // value pass has no q/k operands
     __nv_bfloat16 *Ps = (MODE == MODE_VE) ? Vs : Vs + (size_t)LP * sv;        // energy pass has no V / P
-    __nv_bfloat16 *Xs = Ps + (size_t)LP * sp;                                 // FUSE: the output column (bf16, rows of sv elements)
+    __nv_bfloat16 *Xr = Ps + (size_t)LP * sp + ((MODE == MODE_VPV) ? (size_t)(NT / 2) * kStageElems : 0);   // COL / VPV: the raw line
+    __nv_bfloat16 *Xs = Xr + (size_t)LP * sv;                                 // FUSE: the output column (bf16, rows of sv elements)
     const int lines = (MODE == MODE_ROW) ? p.H : p.W;
     const int b = (active ? vb : 0) / lines, line = (active ? vb : 0) % lines;
     const size_t img = (size_t)b * p.H * p.W;
@@ -289,18 +292,28 @@ __global__ void __launch_bounds__(NT * 16 * LPC) attn_mma_kernel(const AttnParam
                 cp_async16(ps_u + (uint32_t)(j * sp + c) * 2, E + (size_t)(j < L ? j : 0) * LP + c, j < L);
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
-            stage_operands<false, true>(w1, p.Cq, gm, LP, tis, kThreads, x_src, Aq, Bk, Vs);
+            stage_operands<false, true, true>(w1, p.Cq, gm, LP, tis, kThreads, x_src, Aq, Bk, Vs, Xr);
             asm volatile("cp.async.wait_group 0;" ::: "memory");
         } else if (MODE == MODE_VE) {
-            stage_operands<true, false>(w1, p.Cq, gm, LP, tis, kThreads, x_src, Aq, Bk, Vs);
+            stage_operands<true, false, false>(w1, p.Cq, gm, LP, tis, kThreads, x_src, Aq, Bk, Vs, Xr);
+        } else if (MODE == MODE_COL) {
+            stage_operands<true, true, true>(w1, p.Cq, gm, LP, tis, kThreads, x_src, Aq, Bk, Vs, Xr);
         } else {
-            stage_operands<true, true>(w1, p.Cq, gm, LP, tis, kThreads, x_src, Aq, Bk, Vs);
+            stage_operands<true, true, false>(w1, p.Cq, gm, LP, tis, kThreads, x_src, Aq, Bk, Vs, Xr);
         }
     }
     __syncthreads();
 
     const int row0 = warp * 16;                                  // this warp's query rows
     float m_row[2] = {0.0f, 0.0f}, s_row[2] = {1.0f, 1.0f};
+    float2 rstat[2] = {make_float2(0.0f, 1.0f), make_float2(0.0f, 1.0f)};
+    if (MODE == MODE_COL && active) {                             // row-pass statistics of my query rows: in flight during the energy product
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+            const int i = row0 + g + 8 * hh;
+            if (i < L) rstat[hh] = __ldg(reinterpret_cast<const float2 *>(row_stats + pix_of(i) * 2));
+        }
+    }
     if (MODE != MODE_VPV && active) {
         float e[NT][4];
         line_energies<NT>(e, Aq, Bk, sq, KQ, row0, lane);
@@ -353,8 +366,7 @@ __global__ void __launch_bounds__(NT * 16 * LPC) attn_mma_kernel(const AttnParam
                 const int i = row0 + g + 8 * hh;
                 float aw = 0.0f;
                 if (i < L) {
-                    const float2 ms = *reinterpret_cast<const float2 *>(row_stats + pix_of(i) * 2);
-                    const float mw = ms.x, sw = ms.y, mh = m_row[hh], sh = s_row[hh];
+                    const float mw = rstat[hh].x, sw = rstat[hh].y, mh = m_row[hh], sh = s_row[hh];
                     const float m = fmaxf(mh, mw);
                     const float fh = ex2_fast(mh - m), fw = ex2_fast(mw - m);          // (max, sum) of both passes are in the log2 domain
                     const float inv = 1.0f / (sh * fh + sw * fw);
@@ -377,6 +389,14 @@ __global__ void __launch_bounds__(NT * 16 * LPC) attn_mma_kernel(const AttnParam
             float o[4][4];
 #pragma unroll
             for (int ct = 0; ct < 4; ++ct) o[ct][0] = o[ct][1] = o[ct][2] = o[ct][3] = 0.0f;
+            uint4 pwv[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+            if (MODE == MODE_COL) {                               // row partials of this chunk: in flight during the P.V product
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const int idx = lane + 32 * k, i = row0 + (idx >> 2);
+                    if (i < L) pwv[k] = __ldg(reinterpret_cast<const uint4 *>(reinterpret_cast<const __nv_bfloat16 *>(p.scratch) + pix_of(i) * C + c0 + (idx & 3) * 8));
+                }
+            }
 #pragma unroll
             for (int kt = 0; kt < NT / 2; ++kt) {
                 uint32_t a0, a1, a2, a3;
@@ -409,13 +429,9 @@ __global__ void __launch_bounds__(NT * 16 * LPC) attn_mma_kernel(const AttnParam
                     // un-normalised row partial O_W as bf16 [pix][C] (it re-enters a bf16 result scaled by gamma)
                     *reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(p.scratch) + px * C + c) = oh;
                 } else {
-                    const uint4 xw = __ldg(reinterpret_cast<const uint4 *>(p.x + px * p.x_cs + p.x_off + c));
-                    uint4 pw = make_uint4(0, 0, 0, 0);
-                    float aw = 0.0f;
-                    if (MODE == MODE_COL) {
-                        pw = *reinterpret_cast<const uint4 *>(reinterpret_cast<const __nv_bfloat16 *>(p.scratch) + px * C + c);
-                        aw = wsc[r];
-                    }
+                    const uint4 xw = *reinterpret_cast<const uint4 *>(Xr + (size_t)i * sv + c);
+                    const uint4 pw = pwv[k];
+                    const float aw = (MODE == MODE_COL) ? wsc[r] : 0.0f;
                     const uint32_t ohw[4] = {oh.x, oh.y, oh.z, oh.w}, xww[4] = {xw.x, xw.y, xw.z, xw.w}, pww[4] = {pw.x, pw.y, pw.z, pw.w};
                     uint32_t res[4];
 #pragma unroll
@@ -435,7 +451,7 @@ __global__ void __launch_bounds__(NT * 16 * LPC) attn_mma_kernel(const AttnParam
         __syncthreads();                                         // all staging tiles (in the Aq / Bk region) are dead, Xs is complete
         if (active) {
             auto xs_src = [&](int pi, int d) -> uint4 { return *reinterpret_cast<const uint4 *>(Xs + (size_t)pi * sv + d * 8); };
-            stage_operands<true, false>(w2, p.Cq, gm, LP, tis, kThreads, xs_src, Aq, Bk, Vs);
+            stage_operands<true, false, false>(w2, p.Cq, gm, LP, tis, kThreads, xs_src, Aq, Bk, Vs, Xr);
         }
         __syncthreads();
         if (active) {
@@ -487,6 +503,7 @@ int launch_nt(const AttnParams &p, const AttnW &w2, int L, cudaStream_t st) {
     if (MODE != MODE_VPV) smem += 2 * (size_t)gm.LP * gm.sq * 2;
     if (MODE != MODE_VE) smem += (size_t)gm.LP * gm.sv * 2 + (size_t)gm.LP * gm.sp * 2;
     if (MODE == MODE_VPV) smem += (size_t)(NT / 2) * kStageElems * 2;          // row / column passes stage in the dead q/k operand region
+    if (MODE == MODE_COL || MODE == MODE_VPV) smem += (size_t)gm.LP * gm.sv * 2;   // the raw line (the "+ x" of the epilogue)
     if (FUSE) smem += (size_t)gm.LP * gm.sv * 2;                               // the output column kept for the fused energy pass
     smem = (smem + 15) & ~size_t(15);
     if (smem * LPC > 227 * 1024) return 1;

@@ -78,15 +78,32 @@ def nms_padded(prediction, conf_thres=0.25, iou_thres=0.45, classes=None, agnost
     return out, counts
 
 
+def _with_apriori_labels(prediction, labels):
+    B, n, no = prediction.shape
+    if len(labels) != B:
+        raise ValueError('labels: one (n_i, 5) tensor per image')
+    lmax = max(len(l) for l in labels)
+    extra = torch.zeros((B, lmax, no), dtype=torch.float32, device=prediction.device)
+    extra[:, :, 4] = float('-inf')
+    for b, l in enumerate(labels):
+        l = torch.as_tensor(l, dtype=torch.float32, device=prediction.device).reshape(-1, 5)
+        if len(l):
+            extra[b, :len(l), :4] = l[:, 1:5]
+            extra[b, :len(l), 4] = 1.0
+            extra[b, torch.arange(len(l), device=l.device), l[:, 0].long() + 5] = 1.0
+    return torch.cat([prediction.detach().float(), extra], 1)
+
+
 def non_max_suppression(prediction, conf_thres=0.25, iou_thres=0.45, classes=None, agnostic=False, multi_label=False,
                         labels=()):
     """Runs NMS on inference results; returns a list of (n, 6) tensors [xyxy, conf, cls] per image, like the reference.
 
     Differences from the reference, by design: no 10 s ``time_limit`` break, and the > 30000-row cut is the stable one.
-    ``labels`` (test.py --save-hybrid autolabelling) is outside the deployed path and rejected.
+    ``labels`` (test.py --save-hybrid autolabelling, general.py:981-987): per image the label rows (cls, x, y, w, h) are appended
+    behind the candidates as [box, conf = 1, one-hot class] rows of the dense tensor (unused rows: obj = -inf, never pass).
     """
-    if labels is not None and len(labels):
-        raise NotImplementedError('apriori labels (save_hybrid) are not part of the deployed hot path')
+    if labels is not None and len(labels) and any(len(l) for l in labels):
+        prediction = _with_apriori_labels(prediction, labels)
     out, counts = nms_padded(prediction, conf_thres, iou_thres, classes, agnostic, multi_label)
     cnt = counts.cpu().tolist()                       # the one device->host read of this call
     return [out[i, :c] for i, c in enumerate(cnt)]

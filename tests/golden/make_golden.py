@@ -17,6 +17,8 @@ What it does
   5. runs the reference head with ``include_nms`` (IDetect.convert(), models/yolo.py:189-199) and ``end2end`` set on
      the same 64x64 input                                               -> convert_64.npz
      (``python tests/golden/make_golden.py --only-convert`` regenerates just this file)
+  6. runs the reference ``non_max_suppression(..., labels=[...])`` (apriori labels of test.py --save-hybrid, general.py:981-987)
+                                                                        -> nms_labels.npz   (``--only-labels``)
 """
 import contextlib
 import io
@@ -122,6 +124,32 @@ def main():
         json.dump(keys, f)
     np.savez_compressed(os.path.join(HERE, 'fold_digest.npz'),
                         **{k: digest(v) for k, v in fsd.items() if v.dtype.is_floating_point})
+
+    # 6. apriori labels (test.py --save-hybrid autolabelling, general.py:981-987): label rows are appended AFTER the confidence filter
+    if '--only-labels' in sys.argv or '--only-convert' not in sys.argv:
+        g = torch.Generator().manual_seed(77)
+        B, N, nc = 3, 400, 4
+        cxy = torch.rand(B, N, 2, generator=g) * 320
+        wh = torch.rand(B, N, 2, generator=g) * 60 + 8
+        lp = torch.cat([cxy, wh, torch.rand(B, N, 1, generator=g), torch.rand(B, N, nc, generator=g)], 2)
+        labels = []
+        for b, nl in enumerate((5, 0, 2)):                                 # image 1 has no labels
+            l = torch.cat([torch.randint(0, nc, (nl, 1), generator=g).float(), lp[b, :nl, :4] + 3.0], 1)   # overlapping real candidates
+            labels.append(l)
+        blob = {'pred': lp.numpy().astype(np.float32)}
+        for ci, kw in enumerate((dict(conf_thres=0.25, iou_thres=0.45), dict(conf_thres=0.1, iou_thres=0.6, multi_label=True))):
+            outs = []
+            for b in range(B):
+                outs += ref_nms(lp[b:b + 1].clone(), labels=[labels[b]], **kw)
+            blob[f'c{ci}.counts'] = np.array([o.shape[0] for o in outs], dtype=np.int32)
+            blob[f'c{ci}.out'] = torch.cat(outs, 0).numpy().astype(np.float32)
+            blob[f'c{ci}.kw'] = np.frombuffer(json.dumps(kw).encode(), dtype=np.uint8)
+        for b in range(B):
+            blob[f'labels{b}'] = labels[b].numpy().astype(np.float32)
+        np.savez_compressed(os.path.join(HERE, 'nms_labels.npz'), **blob)
+        print('nms_labels.npz', [blob[f'c{c}.counts'].tolist() for c in range(2)])
+        if '--only-labels' in sys.argv:
+            return
 
     # 5. alternative output contracts of IDetect.fuseforward (yolo.py:158-166) on the tag-'64' input
     x = torch.rand(1, 3, 64, 64, generator=torch.Generator().manual_seed(5))

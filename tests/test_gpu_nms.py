@@ -181,3 +181,16 @@ def test_decode_filter_mask_and_detections(B, H, W, nc, conf):
     assert int((pred[..., 4] > conf).sum()) > 0
     for c2, iou in ((conf, 0.45), (max(conf, 0.3), 0.65)):
         _same(R.non_max_suppression(pred, c2, iou), R.non_max_suppression(plain, c2, iou), ('decode_filter', B, H, W, nc, c2))
+
+
+def test_apriori_labels_match_reference():
+    """non_max_suppression(labels=[...]) (test.py --save-hybrid, general.py:981-987) against the reference-minted fixture."""
+    import repyolo_b200 as R
+    g = np.load(os.path.join(GOLDEN, 'nms_labels.npz'))
+    pred = torch.from_numpy(g['pred']).cuda()
+    labels = [torch.from_numpy(g[f'labels{b}']).cuda() for b in range(pred.shape[0])]
+    for c in range(2):
+        kw = json.loads(bytes(g[f'c{c}.kw']).decode())
+        outs = R.non_max_suppression(pred, labels=labels, **kw)
+        assert [o.shape[0] for o in outs] == g[f'c{c}.counts'].tolist()
+        assert torch.cat(outs, 0).cpu().numpy().tobytes() == g[f'c{c}.out'].tobytes()

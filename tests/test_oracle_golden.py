@@ -127,3 +127,16 @@ def test_convert_and_end2end_contracts_match_reference(oracle_model):
     box, score = O.convert(torch.from_numpy(g['pred']))
     assert np.array_equal(box.numpy(), g['box']) and np.array_equal(score.numpy(), g['score'])
     assert np.array_equal(g['end2end'], g['pred'])
+
+
+def test_nms_apriori_labels_match_reference():
+    """general.py:981-987 (test.py --save-hybrid): label rows appended behind the filtered candidates; fixture minted from the
+    reference's own non_max_suppression(labels=[...]) by tests/golden/make_golden.py step 6."""
+    g = np.load(os.path.join(GOLDEN, 'nms_labels.npz'))
+    pred = torch.from_numpy(g['pred'])
+    labels = [torch.from_numpy(g[f'labels{b}']) for b in range(pred.shape[0])]
+    for c in range(2):
+        kw = json.loads(bytes(g[f'c{c}.kw']).decode())
+        outs = nms_oracle.non_max_suppression(pred, labels=labels, **kw)
+        assert [o.shape[0] for o in outs] == g[f'c{c}.counts'].tolist()
+        assert torch.cat(outs, 0).numpy().tobytes() == g[f'c{c}.out'].tobytes()
