@@ -244,7 +244,7 @@ __device__ __forceinline__ void store_energies(const float (&e)[NT][4], __nv_bfl
 // here on the column kept in shared memory (w2 = the vertical module's parameters) instead of a launch that re-reads it.
 // (forcing 5 CTAs / SM through __launch_bounds__ -- 72 registers, ~80 B of spills -- was measured slower: 0.74 vs 0.68 ms)
 template <int MODE, int NT, int LPC, bool FUSE>
-__global__ void __launch_bounds__(NT * 16 * LPC) attn_mma_kernel(const AttnParams p, const AttnW w1, const AttnW w2, const Geom gm,
+__global__ void __launch_bounds__(NT * 16 * LPC, ((MODE == MODE_ROW || MODE == MODE_COL) && NT <= 12) ? 640 / (NT * 16 * LPC) : 1) attn_mma_kernel(const AttnParams p, const AttnW w1, const AttnW w2, const Geom gm,
                                                                  int total_lines, size_t slot_bytes) {
     pdl_trigger();
     pdl_wait();
@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(NT * 16 * LPC) attn_mma_kernel(const AttnParam
                 cp_async16(ps_u + (uint32_t)(j * sp + c) * 2, E + (size_t)(j < L ? j : 0) * LP + c, j < L);
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
-            stage_operands<false, true, true>(w1, p.Cq, gm, LP, tis, kThreads, x_src, Aq, Bk, Vs, Xr);
+            stage_operands<false, true, false>(w1, p.Cq, gm, LP, tis, kThreads, x_src, Aq, Bk, Vs, Xr);
             asm volatile("cp.async.wait_group 0;" ::: "memory");
         } else if (MODE == MODE_VE) {
             stage_operands<true, false, false>(w1, p.Cq, gm, LP, tis, kThreads, x_src, Aq, Bk, Vs, Xr);
@@ -390,11 +390,15 @@ __global__ void __launch_bounds__(NT * 16 * LPC) attn_mma_kernel(const AttnParam
 #pragma unroll
             for (int ct = 0; ct < 4; ++ct) o[ct][0] = o[ct][1] = o[ct][2] = o[ct][3] = 0.0f;
             uint4 pwv[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
-            if (MODE == MODE_COL) {                               // row partials of this chunk: in flight during the P.V product
+            if (MODE == MODE_COL || MODE == MODE_VPV) {           // row partials (COL) / x (VPV) of this chunk: in flight during the P.V product
 #pragma unroll
                 for (int k = 0; k < 2; ++k) {
                     const int idx = lane + 32 * k, i = row0 + (idx >> 2);
-                    if (i < L) pwv[k] = __ldg(reinterpret_cast<const uint4 *>(reinterpret_cast<const __nv_bfloat16 *>(p.scratch) + pix_of(i) * C + c0 + (idx & 3) * 8));
+                    if (i >= L) continue;
+                    if (MODE == MODE_COL)
+                        pwv[k] = __ldg(reinterpret_cast<const uint4 *>(reinterpret_cast<const __nv_bfloat16 *>(p.scratch) + pix_of(i) * C + c0 + (idx & 3) * 8));
+                    else
+                        pwv[k] = __ldg(reinterpret_cast<const uint4 *>(p.x + pix_of(i) * p.x_cs + p.x_off + c0 + (idx & 3) * 8));
                 }
             }
 #pragma unroll
@@ -429,8 +433,8 @@ __global__ void __launch_bounds__(NT * 16 * LPC) attn_mma_kernel(const AttnParam
                     // un-normalised row partial O_W as bf16 [pix][C] (it re-enters a bf16 result scaled by gamma)
                     *reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(p.scratch) + px * C + c) = oh;
                 } else {
-                    const uint4 xw = *reinterpret_cast<const uint4 *>(Xr + (size_t)i * sv + c);
-                    const uint4 pw = pwv[k];
+                    const uint4 xw = (MODE == MODE_COL) ? *reinterpret_cast<const uint4 *>(Xr + (size_t)i * sv + c) : pwv[k];
+                    const uint4 pw = (MODE == MODE_COL) ? pwv[k] : make_uint4(0, 0, 0, 0);
                     const float aw = (MODE == MODE_COL) ? wsc[r] : 0.0f;
                     const uint32_t ohw[4] = {oh.x, oh.y, oh.z, oh.w}, xww[4] = {xw.x, xw.y, xw.z, xw.w}, pww[4] = {pw.x, pw.y, pw.z, pw.w};
                     uint32_t res[4];
@@ -503,7 +507,7 @@ int launch_nt(const AttnParams &p, const AttnW &w2, int L, cudaStream_t st) {
     if (MODE != MODE_VPV) smem += 2 * (size_t)gm.LP * gm.sq * 2;
     if (MODE != MODE_VE) smem += (size_t)gm.LP * gm.sv * 2 + (size_t)gm.LP * gm.sp * 2;
     if (MODE == MODE_VPV) smem += (size_t)(NT / 2) * kStageElems * 2;          // row / column passes stage in the dead q/k operand region
-    if (MODE == MODE_COL || MODE == MODE_VPV) smem += (size_t)gm.LP * gm.sv * 2;   // the raw line (the "+ x" of the epilogue)
+    if (MODE == MODE_COL) smem += (size_t)gm.LP * gm.sv * 2;                   // the raw line (the "+ x" of the epilogue)
     if (FUSE) smem += (size_t)gm.LP * gm.sv * 2;                               // the output column kept for the fused energy pass
     smem = (smem + 15) & ~size_t(15);
     if (smem * LPC > 227 * 1024) return 1;
