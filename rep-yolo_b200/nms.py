@@ -54,12 +54,13 @@ def nms_padded(prediction, conf_thres=0.25, iou_thres=0.45, classes=None, agnost
     multi_label = bool(multi_label) and nc > 1
     if out is None:
         out = torch.empty((B, max_det, 6), dtype=torch.float32, device=p.device)
-    if counts is None:
-        counts = torch.zeros((B,), dtype=torch.int32, device=p.device)
+    if counts is None:                                  # ry_nms writes every entry: no fill kernel on the hot path
+        counts = torch.empty((B,), dtype=torch.int32, device=p.device)
     if (tuple(out.shape) != (B, max_det, 6) or out.dtype != torch.float32 or not out.is_contiguous() or out.device != p.device or
             tuple(counts.shape) != (B,) or counts.dtype != torch.int32 or not counts.is_contiguous() or counts.device != p.device):
         raise ValueError('nms_padded: out must be contiguous fp32 [B, max_det, 6] and counts int32 [B] on the prediction device')
     if B == 0 or n == 0:
+        counts.zero_()
         return out, counts
     if classes is not None and len(classes) == 0:
         counts.zero_()
