@@ -185,6 +185,11 @@ int ry_letterbox_u8(const uint8_t *src_hwc, int H0, int W0, int src_row_bytes, u
                     int left, int top, const int32_t *pad_value3_host, int planar_rgb, void *stream);
 int ry_scale_coords(float *coords, const int32_t *count_dev, int n_max, int row_stride, float pad_x, float pad_y, float gain, int w0,
                     int h0, int round_result, void *stream);
+/* ry_nchw_to_nhwc_bf16 <- the layout IDetect.fuseforward's callers hand over (models/yolo.py:135: a list of fp32 NCHW maps) -> channels
+ *                     [dst_c_off, dst_c_off + C) of an NHWC bf16 tensor with dst_channels channels per pixel (a plan tensor located
+ *                     with ry_plan_tensor_info).  C, dst_c_off, dst_channels: multiples of 8. */
+int ry_nchw_to_nhwc_bf16(const float *src_nchw, int B, int C, int H, int W, void *dst_nhwc_bf16, int dst_channels, int dst_c_off,
+                         void *stream);
 
 #ifdef __cplusplus
 }

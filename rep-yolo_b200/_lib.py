@@ -35,7 +35,7 @@ class OpDesc(C.Structure):
 
 EXPORTS = ['ry_abi_version', 'ry_abi_sizeof', 'ry_last_error', 'ry_plan_create', 'ry_plan_destroy', 'ry_plan_workspace_bytes',
            'ry_plan_bind', 'ry_plan_tensor_info', 'ry_plan_num_candidates', 'ry_plan_launch_count', 'ry_forward',
-           'ry_run_ops', 'ry_plan_set_image_dtype', 'ry_plan_set_profiling', 'ry_plan_op_times', 'ry_nms_workspace_bytes', 'ry_nms_launch_count', 'ry_nms', 'ry_decode_filter', 'ry_nms_filtered', 'ry_letterbox_u8', 'ry_scale_coords']
+           'ry_run_ops', 'ry_plan_set_image_dtype', 'ry_plan_set_profiling', 'ry_plan_op_times', 'ry_nms_workspace_bytes', 'ry_nms_launch_count', 'ry_nms', 'ry_decode_filter', 'ry_nms_filtered', 'ry_letterbox_u8', 'ry_scale_coords', 'ry_nchw_to_nhwc_bf16']
 
 _lib = None
 ABI_VERSION = 5
@@ -77,6 +77,7 @@ def lib():
     L.ry_nms_filtered.argtypes = [vp, vp, i32, i32, i32, C.c_float, C.c_double, vp, i32, i32, i32, i32, i32, vp, vp, vp, sz, vp]
     L.ry_letterbox_u8.argtypes = [vp, i32, i32, i32, vp, i32, i32, i32, i32, i32, i32, C.POINTER(i32), i32, vp]
     L.ry_scale_coords.argtypes = [vp, vp, i32, i32, C.c_float, C.c_float, C.c_float, i32, i32, i32, vp]
+    L.ry_nchw_to_nhwc_bf16.argtypes = [vp, i32, i32, i32, i32, vp, i32, i32, vp]
     for name in EXPORTS:
         if name not in ('ry_last_error', 'ry_plan_destroy', 'ry_abi_version', 'ry_abi_sizeof'):
             getattr(L, name).restype = i32

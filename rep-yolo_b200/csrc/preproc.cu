@@ -6,7 +6,10 @@
 //   fx = float((dx + 0.5) * scale_x - 0.5); sx = floor(fx); fx -= sx; border columns clamp sx and zero fx; rows clamp the index
 //   a = (rint((1 - fx) * 2048), rint(fx * 2048));  H = S[sx] * a0 + S[sx + 1] * a1;
 //   dst = (((b0 * (H0 >> 4)) >> 16) + ((b1 * (H1 >> 4)) >> 16) + 2) >> 2
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
+
+#include <algorithm>
 #include <stdint.h>
 
 #include "common.cuh"
@@ -89,6 +92,24 @@ __global__ void __launch_bounds__(256) scale_coords_kernel(float *coords, const 
     c[0] = x1; c[1] = y1; c[2] = x2; c[3] = y2;
 }
 
+// fp32 NCHW feature map -> a channel range of an NHWC bf16 tensor (IDetect.fuseforward called on its own, models/yolo.py:135: the
+// caller hands over NCHW maps; the head kernels read NHWC bf16).  Lanes walk pixels (coalesced reads of each channel plane),
+// every thread writes the 8 channels of its pixel as one 16-byte vector.
+__global__ void __launch_bounds__(256) nchw_to_nhwc_bf16_kernel(const float *__restrict__ src, int C, size_t hw, size_t npix,
+                                                                 __nv_bfloat16 *__restrict__ dst, int dst_cs, int dst_off) {
+    const int groups = C >> 3;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix * groups; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t pix = i % npix;
+        const int g = (int)(i / npix);
+        const size_t b = pix / hw, r = pix - b * hw;
+        const float *p = src + (b * C + (size_t)g * 8) * hw + r;
+        uint32_t w[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) w[j] = pack_bf16x2(__ldg(p + (size_t)(2 * j) * hw), __ldg(p + (size_t)(2 * j + 1) * hw));
+        *reinterpret_cast<uint4 *>(dst + pix * dst_cs + dst_off + g * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
 }  // namespace
 }  // namespace ry
 
@@ -120,6 +141,20 @@ int ry_scale_coords(float *coords, const int32_t *count_dev, int n_max, int row_
     if (n_max == 0) return 0;
     scale_coords_kernel<<<(n_max + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(coords, count_dev, n_max, row_stride, pad_x, pad_y,
                                                                                        gain, (float)w0, (float)h0, round_result);
+    RY_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int ry_nchw_to_nhwc_bf16(const float *src_nchw, int B, int C, int H, int W, void *dst_nhwc_bf16, int dst_channels, int dst_c_off,
+                         void *stream) {
+    using namespace ry;
+    if (!src_nchw || !dst_nhwc_bf16) RY_FAIL("ry_nchw_to_nhwc_bf16: NULL pointer");
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || (C & 7) || (dst_c_off & 7) || (dst_channels & 7) || dst_c_off + C > dst_channels)
+        RY_FAIL("ry_nchw_to_nhwc_bf16: channel counts / offsets must be multiples of 8 and fit the destination");
+    const size_t hw = (size_t)H * W, npix = (size_t)B * hw, total = npix * (size_t)(C >> 3);
+    const int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)num_sms() * 16);
+    nchw_to_nhwc_bf16_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(src_nchw, C, hw, npix, static_cast<__nv_bfloat16 *>(dst_nhwc_bf16),
+                                                                                 dst_channels, dst_c_off);
     RY_CUDA(cudaGetLastError());
     return 0;
 }

@@ -351,9 +351,18 @@ class Model(nn.Module):
         B, H, W = xs[0].shape[0], xs[0].shape[2] * 8, xs[0].shape[3] * 8
         eng.bind(B, H, W)
         grp = eng.plan_ir.groups[-1]
-        for (_, view), x in zip(grp.inputs, xs):
-            t = eng.tensor(view[0])
-            t[..., view[1]:view[1] + view[2]] = x.permute(0, 2, 3, 1).to(torch.bfloat16)
+        with torch.cuda.device(eng.device):
+            st = torch.cuda.current_stream(eng.device).cuda_stream
+            for (_, view), x in zip(grp.inputs, xs):
+                t = eng.tensor(view[0])
+                if not x.is_cuda or x.device != eng.device:
+                    raise N.NativeError('IDetect.fuseforward: feature maps must be CUDA tensors on the engine device')
+                x = x.detach()
+                if x.dtype != torch.float32 or not x.is_contiguous():
+                    x = x.float().contiguous()
+                # fp32 NCHW (what the reference's callers hand over) -> the head's NHWC bf16 input view, native kernel
+                N.check(N.lib().ry_nchw_to_nhwc_bf16(x.data_ptr(), int(x.shape[0]), int(x.shape[1]), int(x.shape[2]), int(x.shape[3]),
+                                                      t.data_ptr(), int(t.shape[-1]), int(view[1]), C.c_void_p(st)), 'ry_nchw_to_nhwc_bf16')
         pred, raws = eng._outputs(B, H, W)
         eng.run_ops(grp.first_op, grp.last_op, pred=pred, raws=raws)
         for i in range(len(xs)):
