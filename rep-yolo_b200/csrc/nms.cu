@@ -329,14 +329,24 @@ __global__ void __launch_bounds__(kSoloThreads) sort_image_kernel(uint32_t *__re
     const int n = min(counts[b], (int)cap);
     uint32_t *Ka = keys0 + (size_t)b * cap, *Kb = keys1 + (size_t)b * cap;
     uint32_t *Ia = idx0 + (size_t)b * cap, *Ib = idx1 + (size_t)b * cap;
+    __shared__ int skip_pass;
+    int flips = 0;                                       // executed passes so far: the live copy is in buffer (flips & 1)
     for (int pass = 0; pass < 4; ++pass) {
         const int shift = 8 * pass;
-        const uint32_t *Ks = (pass & 1) ? Kb : Ka, *Is = (pass & 1) ? Ib : Ia;     // passes ping-pong: a -> b -> a -> b -> a
-        uint32_t *Kd = (pass & 1) ? Ka : Kb, *Id = (pass & 1) ? Ia : Ib;
+        const uint32_t *Ks = (flips & 1) ? Kb : Ka, *Is = (flips & 1) ? Ib : Ia;   // executed passes ping-pong: a -> b -> a ...
+        uint32_t *Kd = (flips & 1) ? Ka : Kb, *Id = (flips & 1) ? Ia : Ib;
         if (tid < 256) dbase[tid] = 0;
+        if (tid == 0) skip_pass = 0;
         __syncthreads();
         for (int i = tid; i < n; i += kSoloThreads) atomicAdd(&dbase[(Ks[i] >> shift) & 255], 1u);
         __syncthreads();
+        // every key has the same digit (scores of one binade share the top byte; tied scores share all four): the stable
+        // scatter of this pass would be the identity -> skip it
+        if (tid < 256 && dbase[tid] == (uint32_t)n && n > 0) skip_pass = 1;
+        __syncthreads();
+        const bool skip = skip_pass != 0 || n == 0;
+        __syncthreads();                                 // everybody has read the flag before the next pass resets it
+        if (skip) continue;
         {   // exclusive scan of the 256 digit counts (every thread takes part in the block scan; threads >= 256 add zero)
             const int c = tid < 256 ? (int)dbase[tid] : 0;
             int total;
@@ -390,6 +400,10 @@ __global__ void __launch_bounds__(kSoloThreads) sort_image_kernel(uint32_t *__re
             }
             __syncthreads();
         }
+        ++flips;
+    }
+    if (flips & 1) {                                     // an odd number of passes ran: the result is in b, the scan reads a
+        for (int i = tid; i < n; i += kSoloThreads) { Ka[i] = Kb[i]; Ia[i] = Ib[i]; }
     }
 }
 
