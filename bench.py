@@ -139,6 +139,44 @@ def oracle_step(fz, layers, save, x, torch, O, nms_oracle):
     return nms_oracle.non_max_suppression(pred, CONF, IOU)
 
 
+def cpu_arm(args, torch, O):
+    """(step(x) -> detections, kind, description) of the CPU arm.  When tools/make_baseline_ref.py has staged the reference's own
+    models/ utils/ cfg/ into baseline/_ref (git-ignored, travels to the GPU box), the arm is the UNMODIFIED reference:
+    models.yolo.Model(cfg).load_state_dict(weights).fuse().eval() -> forward -> utils.general.non_max_suppression, fp32 on the
+    host cores (kind "reference").  Otherwise the oracle port (kind "port").  Same synthetic weights either way."""
+    layers, save, sd, fz = O.make_model(seed=0, mode=args.init)
+    ref_dir = os.path.join(ROOT, 'baseline', '_ref')
+    if os.path.exists(os.path.join(ref_dir, 'models', 'yolo.py')) and not os.environ.get('RY_BENCH_FORCE_PORT'):
+        try:
+            import logging
+            from tools.run_reference_script import stub_plot_modules
+            stub_plot_modules()                            # matplotlib / seaborn are imported by utils/plots.py at module scope
+            if ref_dir not in sys.path:
+                sys.path.insert(0, ref_dir)
+            logging.disable(logging.CRITICAL)
+            import contextlib
+            import io
+            with contextlib.redirect_stdout(io.StringIO()), torch.no_grad():        # (detect.py:195 runs everything under no_grad)
+                from models.yolo import Model
+                from utils.general import non_max_suppression as ref_nms
+                m = Model(os.path.join(ref_dir, 'cfg', 'training', 'Rep-YOLO.yaml'), ch=3, nc=1)
+                m.load_state_dict(sd, strict=True)
+                m = m.float().fuse().eval()
+            logging.disable(logging.NOTSET)
+
+            def step(x):
+                with torch.no_grad():
+                    return ref_nms(m(x)[0], CONF, IOU)
+            return step, 'reference', 'the reference itself from baseline/_ref (models.yolo.Model.fuse() forward + utils.general.non_max_suppression, fp32)'
+        except Exception as e:                              # noqa: BLE001  (fall back to the port, say why)
+            why = f'{type(e).__name__}: {e}'
+    else:
+        why = 'baseline/_ref not staged'
+    from oracle import nms_oracle
+    nms_oracle.build()
+    return (lambda x: oracle_step(fz, layers, save, x, torch, O, nms_oracle)), 'port', f'oracle port (fp32 oracle forward + oracle NMS; {why})'
+
+
 def run_reference(args):
     import torch
     rank = int(os.environ.get('RANK', '0'))
@@ -147,27 +185,25 @@ def run_reference(args):
     # rank 0 alone runs the CPU arm, so it takes every host core this process may use; torch.distributed.run exports
     # OMP_NUM_THREADS=1, which would otherwise cripple the reference at N > 1 (round-1 verdict)
     torch.set_num_threads(host_cores())
-    from oracle import nms_oracle
     from oracle import repyolo_oracle as O
-    nms_oracle.build()
-    layers, save, sd, fz = O.make_model(seed=0, mode=args.init)
+    step, kind, what = cpu_arm(args, torch, O)
     sample = max(1, min(args.ref_sample, args.batch))
     g = torch.Generator().manual_seed(1000)
     x = torch.rand(sample, 3, args.size, args.size, generator=g)
     for _ in range(args.warmup):
-        oracle_step(fz, layers, save, x, torch, O, nms_oracle)
+        step(x)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        oracle_step(fz, layers, save, x, torch, O, nms_oracle)
+        step(x)
     dt = time.perf_counter() - t0
     v = sample * args.steps / dt
     cores = torch.get_num_threads()
-    desc = f'{sample} of the {args.batch} images of one step per step (fp32 forward + NMS), {args.steps} steps'
+    desc = f'{sample} of the {args.batch} images of one step per step, {args.steps} steps; {what}'
     line = {'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': 'images/s', 'n_gpus': args.gpus, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': workload_config(args),
-            'cpu_baseline': {'value': v, 'unit': 'images/s', 'cores': cores, 'kind': 'port', 'sample': desc,
+            'cpu_baseline': {'value': v, 'unit': 'images/s', 'cores': cores, 'kind': kind, 'sample': desc,
                              'host_cpus': os.cpu_count()},
             'e2e': {'value': v, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(line), flush=True)
@@ -504,21 +540,19 @@ def run_native(args):
         if gather_ok is not None:
             line['gather_ok'] = gather_ok
         if world == 1 and not args.no_cpu_baseline:
-            from oracle import nms_oracle
-            nms_oracle.build()
             torch.set_num_threads(host_cores())
+            cstep, ckind, cwhat = cpu_arm(args, torch, O)
             n = max(1, min(args.ref_sample, B))
             xs = host[0][:n].clone()
-            oracle_step(fz, layers, save, xs[:1], torch, O, nms_oracle)
+            cstep(xs[:1])
             t0 = time.perf_counter()
             reps = 0
             while reps < 2 or (time.perf_counter() - t0 < 10.0 and reps < 20):
-                oracle_step(fz, layers, save, xs, torch, O, nms_oracle)
+                cstep(xs)
                 reps += 1
             dt = time.perf_counter() - t0
-            line['cpu_baseline'] = {'value': n * reps / dt, 'unit': 'images/s', 'cores': torch.get_num_threads(), 'kind': 'port',
-                                    'sample': f'{reps} x {n} images of the step batch (fp32 oracle forward + oracle NMS)',
-                                    'host_cpus': os.cpu_count()}
+            line['cpu_baseline'] = {'value': n * reps / dt, 'unit': 'images/s', 'cores': torch.get_num_threads(), 'kind': ckind,
+                                    'sample': f'{reps} x {n} images of the step batch; {cwhat}', 'host_cpus': os.cpu_count()}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
