@@ -260,8 +260,8 @@ __global__ void __launch_bounds__(NT * 16 * LPC, ((MODE == MODE_ROW || MODE == M
     __nv_bfloat16 *Aq = reinterpret_cast<__nv_bfloat16 *>(sm_raw);
     __nv_bfloat16 *Bk = Aq + (size_t)LP * sq;
     __nv_bfloat16 *Vs = (MODE == MODE_VPV) ? Aq : Bk + (size_t)LP * sq;      // value pass has no q/k operands
-    __nv_bfloat16 *Ps = (MODE == MODE_VE) ? Vs : Vs + (size_t)LP * sv;        // energy pass has no V / P
-    __nv_bfloat16 *Xr = Ps + (size_t)LP * sp + ((MODE == MODE_VPV) ? (size_t)(NT / 2) * kStageElems : 0);   // COL / VPV: the raw line
+    __nv_bfloat16 *Ps = (MODE == MODE_VE) ? Vs : Vs + (size_t)LP * sv;        // value pass only: P = the energies read back from HBM
+    __nv_bfloat16 *Xr = Ps;                                                   // COL: the raw line (row / column passes keep P in registers)
     __nv_bfloat16 *Xs = Xr + (size_t)LP * sv;                                 // FUSE: the output column (bf16, rows of sv elements)
     const int lines = (MODE == MODE_ROW) ? p.H : p.W;
     const int b = (active ? vb : 0) / lines, line = (active ? vb : 0) % lines;
@@ -306,6 +306,9 @@ __global__ void __launch_bounds__(NT * 16 * LPC, ((MODE == MODE_ROW || MODE == M
 
     const int row0 = warp * 16;                                  // this warp's query rows
     float m_row[2] = {0.0f, 0.0f}, s_row[2] = {1.0f, 1.0f};
+    // P of the row / column passes as the A fragments of the second product, straight from the soft-max registers: the fp32
+    // accumulator layout of two adjacent 8-column tiles of m16n8k16 IS the bf16 A fragment of one 16-wide K step
+    uint32_t pa[NT / 2][4];
     float2 rstat[2] = {make_float2(0.0f, 1.0f), make_float2(0.0f, 1.0f)};
     if (MODE == MODE_COL && active) {                             // row-pass statistics of my query rows: in flight during the energy product
 #pragma unroll
@@ -334,14 +337,13 @@ __global__ void __launch_bounds__(NT * 16 * LPC, ((MODE == MODE_ROW || MODE == M
                 m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
                 m *= kLog2e;                                     // statistics in the log2 domain: p = 2^(e*log2e - m)
                 float s = 0.0f;
-                const int r = row0 + g + 8 * hh;
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt) {
                     const int col = nt * 8 + 2 * t4;
                     const float p0 = col < L ? ex2_fast(fmaf(e[nt][2 * hh], kLog2e, -m)) : 0.0f;
                     const float p1 = col + 1 < L ? ex2_fast(fmaf(e[nt][2 * hh + 1], kLog2e, -m)) : 0.0f;
                     s += p0 + p1;
-                    *reinterpret_cast<uint32_t *>(Ps + (size_t)r * sp + col) = pack_bf16x2(p0, p1);
+                    pa[nt >> 1][(nt & 1) * 2 + hh] = pack_bf16x2(p0, p1);
                 }
                 s += __shfl_xor_sync(0xffffffffu, s, 1);
                 s += __shfl_xor_sync(0xffffffffu, s, 2);
@@ -404,7 +406,8 @@ __global__ void __launch_bounds__(NT * 16 * LPC, ((MODE == MODE_ROW || MODE == M
 #pragma unroll
             for (int kt = 0; kt < NT / 2; ++kt) {
                 uint32_t a0, a1, a2, a3;
-                ldsm_x4(pa_base + kt * 32, a0, a1, a2, a3);
+                if (MODE == MODE_VPV) ldsm_x4(pa_base + kt * 32, a0, a1, a2, a3);
+                else { a0 = pa[kt][0]; a1 = pa[kt][1]; a2 = pa[kt][2]; a3 = pa[kt][3]; }
 #pragma unroll
                 for (int cp = 0; cp < 2; ++cp) {
                     uint32_t b0, b1, b2, b3;
@@ -505,7 +508,8 @@ int launch_nt(const AttnParams &p, const AttnW &w2, int L, cudaStream_t st) {
     gm.e_off = sl.e;
     size_t smem = 0;
     if (MODE != MODE_VPV) smem += 2 * (size_t)gm.LP * gm.sq * 2;
-    if (MODE != MODE_VE) smem += (size_t)gm.LP * gm.sv * 2 + (size_t)gm.LP * gm.sp * 2;
+    if (MODE != MODE_VE) smem += (size_t)gm.LP * gm.sv * 2;
+    if (MODE == MODE_VPV) smem += (size_t)gm.LP * gm.sp * 2;                   // (row / column passes keep P in registers)
     if (MODE == MODE_VPV) smem += (size_t)(NT / 2) * kStageElems * 2;          // row / column passes stage in the dead q/k operand region
     if (MODE == MODE_COL) smem += (size_t)gm.LP * gm.sv * 2;                   // the raw line (the "+ x" of the epilogue)
     if (FUSE) smem += (size_t)gm.LP * gm.sv * 2;                               // the output column kept for the fused energy pass
