@@ -428,7 +428,7 @@ __device__ __forceinline__ void dw5m_stage_load(const Dw5mArgs &a, uint32_t base
     }
 }
 
-__global__ void __launch_bounds__(128, 4) dw5_mma_kernel(const __grid_constant__ Dw5mArgs a) {
+__global__ void __launch_bounds__(128, 5) dw5_mma_kernel(const __grid_constant__ Dw5mArgs a) {
     pdl_trigger();
     extern __shared__ __align__(128) uint8_t dw_smem[];
     const uint32_t smem_u = (uint32_t)__cvta_generic_to_shared(dw_smem);
