@@ -213,7 +213,7 @@ def workload_config(args):
     return {'workload': f'Rep-YOLO fused, batch {args.batch} per GPU at {args.size}x{args.size}, Detect decode + NMS '
                         f'(conf {CONF}, iou {IOU}) in-loop; weights: synthetic {args.init} init (seed 0)',
             'batch_per_gpu': args.batch, 'img_size': args.size, 'conf_thres': CONF, 'iou_thres': IOU,
-            'decode_filter': not getattr(args, 'no_decode_filter', False),
+            'decode_filter': not getattr(args, 'no_decode_filter', False), 'cuda_graph': not getattr(args, 'no_cuda_graph', False),
             'l2_policy': 'inputs larger than L2 (fp32 image batch = %.0f MB, uint8 batch = %.0f MB; activations 5 GB per step)' % (
                 args.batch * 3 * args.size * args.size * 4 / 1e6, args.batch * 3 * args.size * args.size / 1e6),
             'parallelism': f'batch-sharded dp{args.gpus}, NCCL all-gather of [B,300,6] detections' if args.gpus > 1 else 'single GPU'}
@@ -266,6 +266,8 @@ def run_native(args):
     model.fuse()
     # fused decode + confidence filter (ry_decode_filter -> ry_nms_filtered): same pred, byte-identical detections
     model.decode_filter = None if args.no_decode_filter else CONF
+    # the ~160 launches of the forward pass replayed as one CUDA graph (static output slots; the bench feeds fixed input buffers)
+    model.cuda_graph = not args.no_cuda_graph
     g = torch.Generator().manual_seed(1000 + rank)
     n_bufs = 2
     # e2e ships uint8 NCHW images to the device exactly like the reference's detect.py:73-78 (torch.from_numpy(img).to(device),
@@ -374,7 +376,7 @@ def run_native(args):
         if gat is not None:
             gat.side.synchronize()
 
-    e2e_loop(max(2, args.warmup))
+    e2e_loop(max(4, args.warmup + 1))          # (both staging buffers seen twice: their CUDA graphs are captured before the timed region)
     sync_all()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
@@ -442,6 +444,7 @@ def run_native(args):
 
     # ---- roofline: per-op CUDA events over K more steps (conv family vs bf16 peak, memory-bound classes vs HBM peak) ----
     ops = eng.plan_ir.ops
+    model.cuda_graph = False                            # per-op events need the eager launches
     eng.set_profiling(True)
     conv_ms, all_ms, per_op = 0.0, 0.0, [0.0] * len(ops)
     prof_steps = min(args.steps, 5)
@@ -572,6 +575,7 @@ def main():
                          "'calibrated' = SURVEY App. D statistics-calibrated init (realistic candidate counts)")
     ap.add_argument('--ref-sample', type=int, default=4, help='images per step of the CPU reference arm / cpu_baseline')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-cuda-graph', action='store_true', help='eager launches instead of replaying the forward pass as one CUDA graph')
     ap.add_argument('--no-decode-filter', action='store_true', help='plain front end: ry_forward -> ry_nms tests every row of pred')
     ap.add_argument('--no-nms-legs', action='store_true', help='skip the second-init NMS leg (A/B runs)')
     args = ap.parse_args()

@@ -444,3 +444,42 @@ def test_der_block_teacher_forced_batch16_1280(oracle_model):
         outs[1] = y
         outs[2] = O.run_fused_layer(fz, layers[2], y)
     _run_groups_tiled(m, layers, outs, x0, B, H, W, n_ref, want_first_layers=(0, 1))
+
+
+def test_cuda_graph_replay_matches_eager():
+    """Model.cuda_graph: the forward pass replayed as one CUDA graph (static output slots, captured the second time an input
+    address is seen) returns exactly what the eager launches return -- alternating input buffers, with and without the fused
+    decode filter, across a shape change."""
+    import repyolo_b200 as R
+    layers, save, sd, fz = O.make_model(seed=0, mode='calibrated')
+    m = R.Model()
+    m.load_state_dict(sd, strict=True)
+    m.fuse()
+    gen = torch.Generator().manual_seed(77)
+    xs = [torch.rand(2, 3, 128, 160, generator=gen).cuda() for _ in range(2)]
+    want = [m(x)[0].clone() for x in xs]
+    m.cuda_graph = True
+    eng = m.engine('cuda:0')
+    for it in range(8):                                      # calls 0-1 eager (first sight), 2-3 capture, 4+ replay
+        pred, raws = m(xs[it % 2])
+        assert torch.equal(pred, want[it % 2]), it
+        assert len(raws) == 3 and raws[0].shape == (2, 3, 16, 20, 6)
+    assert len(eng._graphs) == 2
+    xs[0].copy_(xs[1])                                       # same address, new content: the replay reads the new content
+    assert torch.equal(m(xs[0])[0], want[1])
+    m.decode_filter = 0.25
+    for it in range(6):
+        pred, _ = m(xs[1])
+        assert torch.equal(pred, want[1]) and hasattr(pred, '_ry_cand')
+        a = R.non_max_suppression(pred, 0.25, 0.45)
+        b = R.non_max_suppression(want[1], 0.25, 0.45)
+        assert all(torch.equal(p, q) for p, q in zip(a, b))
+    m.decode_filter = None
+    y = torch.rand(1, 3, 64, 64, generator=gen).cuda()       # another shape: new engine / binding, graphs of the old one untouched
+    m.cuda_graph = False
+    ref = m(y)[0].clone()
+    m.cuda_graph = True
+    for it in range(4):
+        assert torch.equal(m(y)[0], ref)
+    for it in range(3):
+        assert torch.equal(m(xs[1])[0], want[1])
