@@ -208,6 +208,16 @@ class NativeEngine:
             del pred._ry_cand
         return pred, raws
 
+    def run_ops(self, first, last, image=None, pred=None, raws=(None, None, None)):
+        ptr = lambda t: t.data_ptr() if t is not None else None
+        if image is not None:
+            self._set_image_dtype(image)
+        with torch.cuda.device(self.device):
+            st = torch.cuda.current_stream(self.device).cuda_stream
+            N.check(N.lib().ry_run_ops(self.handle, first, last, ptr(image), ptr(pred), ptr(raws[0]), ptr(raws[1]), ptr(raws[2]),
+                                       C.c_void_p(st)), 'ry_run_ops')
+
+
 class IDetect(_Node):
     """Detect-layer facade (reference models/yolo.py:93-199): attributes + fuseforward on the native head."""
     export = False
