@@ -424,7 +424,7 @@ __device__ __forceinline__ bool iou_gt(float ax1, float ay1, float ax2, float ay
     return ovr >= thr.t_up;
 }
 
-// One CTA per image, steps of kCh = 128 sorted candidates (the 512-candidate step spent its time in a 512 x 512
+// One CTA per image, steps of kCh = 128 sorted candidates (round 1: the 512-candidate step spent its time in a 512 x 512
 // pair mask and a ~100-cycle-per-keep warp scan on ONE SM per image, although max_det = 300 keeps are usually found within
 // the first few hundred candidates).  Per step:
 //   1. kept-list test: kSub = 4 threads per candidate share the (<= max_det) kept boxes, 4 independent IoUs per trip each;

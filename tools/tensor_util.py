@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Tensor-pipe utilisation of the conv family from ncu counters (VERDICT r1 4c).
+"""Tensor-pipe utilisation of the conv family from ncu counters.
 
     ncu --metrics sm__inst_executed_pipe_tensor_subpipe_hmma.sum,sm__cycles_elapsed.avg,sm__cycles_elapsed.avg.per_second,\
 gpu__time_duration.sum --clock-control none -k regex:"conv_umma_kernel|conv_chain_kernel" -s 218 -c 109 --csv \
