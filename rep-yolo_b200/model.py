@@ -194,7 +194,9 @@ class NativeEngine:
                 side = torch.cuda.Stream(self.device)
                 side.wait_stream(cur)
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, stream=side):       # launches only: ry_forward neither allocates nor synchronises
+                # launches only (ry_forward neither allocates nor synchronises); thread-local capture: CUDA calls of other host
+                # threads (a sampler, a data loader) must not invalidate it
+                with torch.cuda.graph(g, stream=side, capture_error_mode='thread_local'):
                     self._launch(x, pred, raws, mask, conf_filter)
                 cur.wait_stream(side)
                 self._graphs[key] = g
